@@ -1,0 +1,271 @@
+// capi.cu -- the extern "C" boundary declared in include/dietgpu_b200.h.
+// Maps the reference's three batch-addressing forms (pointer / stride / split
+// size; ans/BatchProvider.cuh) onto one internal member list, so every kernel
+// sees a single descriptor table uploaded in one copy.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dgb {
+
+Options& options() {
+  static Options o;
+  return o;
+}
+
+static thread_local cudaError_t tlsLastCuda = cudaSuccess;
+void setLastCudaError(cudaError_t e) { tlsLastCuda = e; }
+
+namespace {
+
+bool validFloatType(int ft) { return ft == DGB_FLOAT16 || ft == DGB_BFLOAT16 || ft == DGB_FLOAT32; }
+uint32_t wordBytes(int kind) { return kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u); }
+
+// pointer form
+int buildPointer(uint32_t n, const void* const* in, const uint32_t* size, void* const* out,
+                 std::vector<HostMember>& v) {
+  if (n && (!in || !size || !out)) return DGB_ERR_INVALID_ARG;
+  v.resize(n);
+  for (uint32_t i = 0; i < n; ++i) v[i] = HostMember{in[i], out[i], size[i]};
+  return DGB_OK;
+}
+
+}  // namespace
+}  // namespace dgb
+
+using namespace dgb;
+
+extern "C" {
+
+int dgb_version(void) { return 1; }
+
+const char* dgb_error_string(int code) {
+  switch (code) {
+    case DGB_OK: return "ok";
+    case DGB_ERR_INVALID_ARG: return "invalid argument";
+    case DGB_ERR_TEMP_TOO_SMALL: return "temporary device memory too small";
+    case DGB_ERR_CUDA: return "CUDA runtime error";
+    case DGB_ERR_CHECKSUM: return "checksum mismatch";
+    case DGB_ERR_TOO_LARGE: return "size exceeds format limits";
+    default: return "unknown error";
+  }
+}
+
+int dgb_last_cuda_error(void) { return (int)tlsLastCuda; }
+
+uint32_t dgb_ans_max_compressed_size(uint32_t bytes) {
+  // ans/GpuANSEncode.cu:13-25 (the header overhead is charged for a constant 4096 blocks)
+  uint64_t raw = ansOverhead(kBlockBytes);
+  raw += (uint64_t)roundUp(kBlockBytes + kBlockBytes / 4u, 16u) * divUp(bytes, kBlockBytes);
+  return (uint32_t)roundUp64(raw, 16);
+}
+
+uint32_t dgb_float_max_compressed_size(int ft, uint32_t n) {
+  if (!validFloatType(ft)) return 0;
+  return kFloatHeaderBytes + dgb_ans_max_compressed_size(n) + floatNonCompBytes(ft, n);
+}
+
+size_t dgb_ans_encode_temp_bytes(uint32_t n, uint32_t maxBytes) {
+  return encodeTempBytes(kKindBytes, n, maxBytes);
+}
+size_t dgb_ans_decode_temp_bytes(uint32_t n) { return decodeTempBytes(kKindBytes, n); }
+size_t dgb_float_compress_temp_bytes(int ft, uint32_t n, uint32_t maxFloats) {
+  return validFloatType(ft) ? encodeTempBytes(ft, n, maxFloats) : 0;
+}
+size_t dgb_float_decompress_temp_bytes(int ft, uint32_t n, uint32_t /*maxFloats*/) {
+  return validFloatType(ft) ? decodeTempBytes(ft, n) : 0;
+}
+
+// ---- encode ----------------------------------------------------------------
+
+int dgb_ans_encode_pointer(void* temp, size_t tempBytes, int pb, int useChecksum, uint32_t n,
+                           const void* const* in, const uint32_t* inSize,
+                           const uint32_t* histogram_dev, void* const* out, uint32_t* outSize_dev,
+                           void* stream) {
+  std::vector<HostMember> v;
+  int rc = buildPointer(n, in, inSize, out, v);
+  if (rc) return rc;
+  return encodeBatch(kKindBytes, temp, tempBytes, pb, useChecksum != 0, n, v.data(), histogram_dev,
+                     outSize_dev, (cudaStream_t)stream);
+}
+
+int dgb_ans_encode_stride(void* temp, size_t tempBytes, int pb, int useChecksum, uint32_t n,
+                          const void* in_dev, uint32_t inSize, uint32_t inStride,
+                          const uint32_t* histogram_dev, void* out_dev, uint32_t outStride,
+                          uint32_t* outSize_dev, void* stream) {
+  if (n && (!out_dev || (inSize && !in_dev))) return DGB_ERR_INVALID_ARG;
+  std::vector<HostMember> v(n);
+  for (uint32_t i = 0; i < n; ++i)
+    v[i] = HostMember{static_cast<const uint8_t*>(in_dev) + (size_t)i * inStride,
+                      static_cast<uint8_t*>(out_dev) + (size_t)i * outStride, inSize};
+  return encodeBatch(kKindBytes, temp, tempBytes, pb, useChecksum != 0, n, v.data(), histogram_dev,
+                     outSize_dev, (cudaStream_t)stream);
+}
+
+int dgb_ans_encode_split_size(void* temp, size_t tempBytes, int pb, int useChecksum, uint32_t n,
+                              const void* in_dev, const uint32_t* splitSizes,
+                              const uint32_t* histogram_dev, void* out_dev, uint32_t outStride,
+                              uint32_t* outSize_dev, void* stream) {
+  if (n && (!splitSizes || !out_dev)) return DGB_ERR_INVALID_ARG;
+  std::vector<HostMember> v(n);
+  size_t off = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    // ans/GpuANSEncode.cu:132-140: interior splits must keep 4 B alignment
+    if (i + 1 != n && (splitSizes[i] % DGB_ANS_REQUIRED_ALIGNMENT)) return DGB_ERR_INVALID_ARG;
+    v[i] = HostMember{static_cast<const uint8_t*>(in_dev) + off,
+                      static_cast<uint8_t*>(out_dev) + (size_t)i * outStride, splitSizes[i]};
+    off += splitSizes[i];
+  }
+  return encodeBatch(kKindBytes, temp, tempBytes, pb, useChecksum != 0, n, v.data(), histogram_dev,
+                     outSize_dev, (cudaStream_t)stream);
+}
+
+int dgb_float_compress_pointer(void* temp, size_t tempBytes, int ft, int pb, int useChecksum,
+                               uint32_t n, const void* const* in, const uint32_t* inSize,
+                               void* const* out, uint32_t* outSize_dev, void* stream) {
+  if (!validFloatType(ft)) return DGB_ERR_INVALID_ARG;
+  std::vector<HostMember> v;
+  int rc = buildPointer(n, in, inSize, out, v);
+  if (rc) return rc;
+  return encodeBatch(ft, temp, tempBytes, pb, useChecksum != 0, n, v.data(), nullptr, outSize_dev,
+                     (cudaStream_t)stream);
+}
+
+int dgb_float_compress_split_size(void* temp, size_t tempBytes, int ft, int pb, int useChecksum,
+                                  uint32_t n, const void* in_dev, const uint32_t* splitSizes,
+                                  void* out_dev, uint32_t outStride, uint32_t* outSize_dev,
+                                  void* stream) {
+  if (!validFloatType(ft)) return DGB_ERR_INVALID_ARG;
+  if (n && (!splitSizes || !out_dev)) return DGB_ERR_INVALID_ARG;
+  std::vector<HostMember> v(n);
+  size_t off = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    v[i] = HostMember{static_cast<const uint8_t*>(in_dev) + off * wordBytes(ft),
+                      static_cast<uint8_t*>(out_dev) + (size_t)i * outStride, splitSizes[i]};
+    off += splitSizes[i];
+  }
+  return encodeBatch(ft, temp, tempBytes, pb, useChecksum != 0, n, v.data(), nullptr, outSize_dev,
+                     (cudaStream_t)stream);
+}
+
+// ---- decode ----------------------------------------------------------------
+
+static int decodePointerCommon(int kind, void* temp, size_t tempBytes, int pb, int useChecksum,
+                               uint32_t n, const void* const* in, void* const* out,
+                               const uint32_t* cap, uint8_t* outSuccess_dev, uint32_t* outSize_dev,
+                               uint8_t* mismatchHost, void* stream) {
+  if (n && (!in || !out || !cap)) return DGB_ERR_INVALID_ARG;
+  std::vector<HostMember> v(n);
+  for (uint32_t i = 0; i < n; ++i) v[i] = HostMember{in[i], out[i], cap[i]};
+  return decodeBatch(kind, temp, tempBytes, pb, useChecksum != 0, n, v.data(), outSuccess_dev,
+                     outSize_dev, mismatchHost, (cudaStream_t)stream);
+}
+
+static int decodeSplitCommon(int kind, void* temp, size_t tempBytes, int pb, int useChecksum,
+                             uint32_t n, const void* const* in, void* out_dev,
+                             const uint32_t* splitSizes, uint8_t* outSuccess_dev,
+                             uint32_t* outSize_dev, uint8_t* mismatchHost, void* stream) {
+  if (n && (!in || !splitSizes)) return DGB_ERR_INVALID_ARG;
+  std::vector<HostMember> v(n);
+  size_t off = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    v[i] = HostMember{in[i], static_cast<uint8_t*>(out_dev) + off * wordBytes(kind), splitSizes[i]};
+    off += splitSizes[i];
+  }
+  return decodeBatch(kind, temp, tempBytes, pb, useChecksum != 0, n, v.data(), outSuccess_dev,
+                     outSize_dev, mismatchHost, (cudaStream_t)stream);
+}
+
+int dgb_ans_decode_pointer(void* temp, size_t tempBytes, int pb, int useChecksum, uint32_t n,
+                           const void* const* in, void* const* out, const uint32_t* cap,
+                           uint8_t* outSuccess_dev, uint32_t* outSize_dev, uint8_t* mismatchHost,
+                           void* stream) {
+  return decodePointerCommon(kKindBytes, temp, tempBytes, pb, useChecksum, n, in, out, cap,
+                             outSuccess_dev, outSize_dev, mismatchHost, stream);
+}
+
+int dgb_ans_decode_stride(void* temp, size_t tempBytes, int pb, int useChecksum, uint32_t n,
+                          const void* in_dev, uint32_t inStride, void* out_dev, uint32_t outStride,
+                          uint32_t outCapacity, uint8_t* outSuccess_dev, uint32_t* outSize_dev,
+                          uint8_t* mismatchHost, void* stream) {
+  if (n && !in_dev) return DGB_ERR_INVALID_ARG;
+  std::vector<HostMember> v(n);
+  for (uint32_t i = 0; i < n; ++i)
+    v[i] = HostMember{static_cast<const uint8_t*>(in_dev) + (size_t)i * inStride,
+                      static_cast<uint8_t*>(out_dev) + (size_t)i * outStride, outCapacity};
+  return decodeBatch(kKindBytes, temp, tempBytes, pb, useChecksum != 0, n, v.data(), outSuccess_dev,
+                     outSize_dev, mismatchHost, (cudaStream_t)stream);
+}
+
+int dgb_ans_decode_split_size(void* temp, size_t tempBytes, int pb, int useChecksum, uint32_t n,
+                              const void* const* in, void* out_dev, const uint32_t* splitSizes,
+                              uint8_t* outSuccess_dev, uint32_t* outSize_dev, uint8_t* mismatchHost,
+                              void* stream) {
+  return decodeSplitCommon(kKindBytes, temp, tempBytes, pb, useChecksum, n, in, out_dev, splitSizes,
+                           outSuccess_dev, outSize_dev, mismatchHost, stream);
+}
+
+int dgb_float_decompress_pointer(void* temp, size_t tempBytes, int ft, int pb, int useChecksum,
+                                 uint32_t n, const void* const* in, void* const* out,
+                                 const uint32_t* cap, uint8_t* outSuccess_dev,
+                                 uint32_t* outSize_dev, uint8_t* mismatchHost, void* stream) {
+  if (!validFloatType(ft)) return DGB_ERR_INVALID_ARG;
+  return decodePointerCommon(ft, temp, tempBytes, pb, useChecksum, n, in, out, cap, outSuccess_dev,
+                             outSize_dev, mismatchHost, stream);
+}
+
+int dgb_float_decompress_split_size(void* temp, size_t tempBytes, int ft, int pb, int useChecksum,
+                                    uint32_t n, const void* const* in, void* out_dev,
+                                    const uint32_t* splitSizes, uint8_t* outSuccess_dev,
+                                    uint32_t* outSize_dev, uint8_t* mismatchHost, void* stream) {
+  if (!validFloatType(ft)) return DGB_ERR_INVALID_ARG;
+  return decodeSplitCommon(ft, temp, tempBytes, pb, useChecksum, n, in, out_dev, splitSizes,
+                           outSuccess_dev, outSize_dev, mismatchHost, stream);
+}
+
+// ---- info ------------------------------------------------------------------
+
+int dgb_ans_get_compressed_info(void* temp, size_t tempBytes, const void* const* in,
+                                int inIsDevice, uint32_t n, uint32_t* outSizes_dev,
+                                uint32_t* outChecksum_dev, void* stream) {
+  return getInfo(kKindBytes, temp, tempBytes, in, inIsDevice != 0, n, outSizes_dev, nullptr,
+                 outChecksum_dev, (cudaStream_t)stream);
+}
+
+int dgb_float_get_compressed_info(void* temp, size_t tempBytes, const void* const* in,
+                                  int inIsDevice, uint32_t n, uint32_t* outSizes_dev,
+                                  uint32_t* outTypes_dev, uint32_t* outChecksum_dev, void* stream) {
+  return getInfo(kKindF16, temp, tempBytes, in, inIsDevice != 0, n, outSizes_dev, outTypes_dev,
+                 outChecksum_dev, (cudaStream_t)stream);
+}
+
+// ---- options ---------------------------------------------------------------
+
+static int* optionSlot(const char* name) {
+  Options& o = options();
+  if (!name) return nullptr;
+  if (!std::strcmp(name, "decode_stage")) return &o.decode_stage;
+  if (!std::strcmp(name, "decode_warps")) return &o.decode_warps;
+  if (!std::strcmp(name, "encode_warps")) return &o.encode_warps;
+  if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
+  if (!std::strcmp(name, "hist_mode")) return &o.hist_mode;
+  return nullptr;
+}
+
+int dgb_set_option(const char* name, int value) {
+  int* s = optionSlot(name);
+  if (!s) return DGB_ERR_INVALID_ARG;
+  *s = value;
+  return DGB_OK;
+}
+
+int dgb_get_option(const char* name, int* value) {
+  int* s = optionSlot(name);
+  if (!s || !value) return DGB_ERR_INVALID_ARG;
+  *value = *s;
+  return DGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+// common.cuh -- wire-format constants, device helpers and the internal host
+// interface shared by the codec translation units.
+//
+// Wire format: identical to the reference's (ans/GpuANSUtils.cuh:67-227 and
+// float/GpuFloatUtils.cuh:26-74, paths relative to /root/reference/dietgpu/).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dietgpu_b200.h"
+
+namespace dgb {
+
+// ---- format constants ------------------------------------------------------
+constexpr uint32_t kBlockBytes = 4096;   // ans/GpuANSUtils.cuh:37
+constexpr uint32_t kRowsPerBlock = kBlockBytes / 32;
+constexpr uint32_t kNumSymbols = 256;
+constexpr uint32_t kStateMin = 1u << 15; // ans/GpuANSUtils.cuh:46-49
+constexpr uint32_t kAnsMagicVersion = (0xd00du << 16) | 1u;   // :52-55,105-107
+constexpr uint32_t kFloatMagicVersion = (0xf00fu << 16) | 1u; // float/GpuFloatUtils.cuh:20-29
+constexpr uint32_t kAnsHeaderBytes = 32;
+constexpr uint32_t kAnsPdfBytes = 512;
+constexpr uint32_t kFloatHeaderBytes = 16;
+
+__host__ __device__ constexpr uint32_t divUp(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+__host__ __device__ constexpr uint32_t roundUp(uint32_t a, uint32_t b) { return divUp(a, b) * b; }
+__host__ __device__ constexpr uint64_t roundUp64(uint64_t a, uint64_t b) { return (a + b - 1) / b * b; }
+
+// ans/GpuANSUtils.cuh:68-81
+__host__ __device__ constexpr uint32_t ansOverhead(uint32_t numBlocks) {
+  return kAnsHeaderBytes + kAnsPdfBytes + 128u * numBlocks + 8u * roundUp(numBlocks, 2u);
+}
+
+// float/GpuFloatUtils.cuh:123-127,163-167,194-203 (bytes of the stored,
+// non-compressed part, 16 B padded)
+__host__ __device__ constexpr uint32_t floatNonCompBytes(int ft, uint32_t n) {
+  return ft == DGB_FLOAT32 ? 2u * roundUp(n, 8u) + roundUp(n, 16u) : roundUp(n, 16u);
+}
+
+// Worst-case u16 words one 4 KiB block can emit: every symbol costs at most
+// probBits bits (a symbol of pdf 1), so 4096*pb/16 words; +8 for 16 B padding.
+__host__ __device__ constexpr uint32_t maxBlockWords(int pb) { return 256u * (uint32_t)pb + 8u; }
+
+// ---- per-member descriptor (device), built on the host in one upload -------
+enum CodecKind : int { kKindBytes = 0, kKindF16 = DGB_FLOAT16, kKindBF16 = DGB_BFLOAT16, kKindF32 = DGB_FLOAT32 };
+
+struct MemberDesc {
+  const void* in;     // encode: raw input (bytes / float words); decode: archive
+  void* out;          // encode: archive; decode: output
+  uint32_t size;      // encode: input size (bytes, or float WORDS); decode: capacity (same unit)
+  uint32_t work0;     // first flat work item (chunk / ticket) of this member
+};
+static_assert(sizeof(MemberDesc) == 24, "");
+
+// ---- encoder symbol table entry (one per symbol, 16 B, shared memory) ------
+// x: thr   = pdf << (31 - pb)      renormalise when state >= thr
+// y: magic                           ans/GpuANSStatistics.cuh:343-358
+// z: shift | (2^pb - pdf) << 8       shift in the low byte (used with shf.wrap)
+// w: cdf
+struct __align__(16) EncEntry {
+  uint32_t thr, magic, kmpShift, cdf;
+};
+
+// ---- tuning options (dgb_set_option) ---------------------------------------
+struct Options {
+  int decode_stage = 1;      // 1: stream staged into smem with cp.async.bulk (TMA); 0: direct LDG
+  int decode_warps = 4;      // warps per decode CTA
+  int encode_warps = 8;      // warps per encode CTA (one 4 KiB block each per ticket)
+  int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
+  int hist_mode = 0;         // 0: per-warp smem atomics; 1: per-lane private byte counters
+};
+Options& options();
+
+// ---- host-side internal API (capi.cu -> *.cu) --------------------------------
+struct HostMember {
+  const void* in;
+  void* out;
+  uint32_t size;  // see MemberDesc::size
+};
+
+int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, uint32_t n,
+                const HostMember* members, const uint32_t* histogram_dev, uint32_t* outSize_dev,
+                cudaStream_t stream);
+int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, uint32_t n,
+                const HostMember* members, uint8_t* outSuccess_dev, uint32_t* outSize_dev,
+                uint8_t* mismatchHost, cudaStream_t stream);
+size_t encodeTempBytes(int kind, uint32_t n, uint32_t maxSize);
+size_t decodeTempBytes(int kind, uint32_t n);
+int getInfo(int kind, void* temp, size_t tempBytes, const void* const* in, bool inIsDevice,
+            uint32_t n, uint32_t* outSizes, uint32_t* outTypes, uint32_t* outChecksum,
+            cudaStream_t stream);
+
+void setLastCudaError(cudaError_t e);
+
+#define DGB_CUDA_TRY(expr)                    \
+  do {                                        \
+    cudaError_t _e = (expr);                  \
+    if (_e != cudaSuccess) {                  \
+      ::dgb::setLastCudaError(_e);            \
+      return DGB_ERR_CUDA;                    \
+    }                                         \
+  } while (0)
+
+#ifdef __CUDACC__
+// ---- small device helpers ---------------------------------------------------
+__device__ __forceinline__ uint32_t laneId() {
+  uint32_t l;
+  asm("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
+__device__ __forceinline__ uint32_t laneMaskLt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t laneMaskGe() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_ge;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t smemAddr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + TMA 1-D bulk copy (cp.async.bulk), sm_90+/sm_100a ------------
+__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fenceBarrierInit() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fenceProxyAsync() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DGB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DGB_DONE_%=;\n"
+      "bra DGB_WAIT_%=;\n"
+      "DGB_DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16 B aligned.
+__device__ __forceinline__ void bulkLoad(uint32_t dstSmem, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dstSmem),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulkStore(void* dst, uint32_t srcSmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(srcSmem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulkWaitRead0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulkPrefetchL2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// block-wide exclusive scan of one value per thread for THREADS threads
+// (THREADS multiple of 32, <= 1024).  `warpSums` is smem of THREADS/32 words.
+template <int THREADS>
+__device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t* warpSums,
+                                                       uint32_t* total) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) warpSums[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) {
+    uint32_t s = warpSums[w];
+    if ((uint32_t)w < warp) base += s;
+    tot += s;
+  }
+  if (total) *total = tot;
+  __syncthreads();
+  return base + incl - v;
+}
+#endif  // __CUDACC__
+
+}  // namespace dgb

@@ -1,0 +1,791 @@
+// encode.cu -- batched rANS encode (bytes) and float compress (fp16/bf16/fp32)
+// for sm_100a.  Two launches per call, whatever the batch size:
+//
+//   K1  statsKernel      one pass over the raw input: 256-bin histogram (+ XOR
+//                        checksum; for floats also the exponent split that
+//                        writes the stored bytes straight into the archive and
+//                        the comp bytes into an L2-resident scratch row).  The
+//                        LAST CTA of each member (atomic ticket) normalises the
+//                        histogram, bit-identical to the reference
+//                        (ans/GpuANSStatistics.cuh:178-367), writes the pdf
+//                        into the archive and the encoder table to scratch.
+//   K2  encodeKernel     persistent CTAs take ORDERED tickets of W consecutive
+//                        4 KiB blocks of one member; each warp runs the 32-lane
+//                        interleaved rANS state machine of its block
+//                        (ans/GpuANSEncode.cuh:49-211) into a shared-memory
+//                        staging slot; a decoupled look-back over the tickets
+//                        of the member gives the packed offset, so the words
+//                        go from shared memory straight to their final place
+//                        (the reference's uncoalesced scratch, prefix-sum
+//                        kernels and coalesce kernel -- ans/GpuANSEncode.cuh:
+//                        515-672, ans/BatchPrefixSum.cuh -- do not exist here).
+//
+// The archive produced is field-for-field the reference's (A.4 of SURVEY.md);
+// bits the reference leaves undefined are zero.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dgb {
+
+namespace {
+
+constexpr int kStatsThreads = 256;  // == kNumSymbols: thread <-> symbol in the epilogue
+constexpr int kStatsWarps = kStatsThreads / 32;
+
+struct EncodeScratch {
+  MemberDesc* members;            // [n]
+  uint32_t* hist;                 // [n][256]      (zeroed per call)
+  uint32_t* histDone;             // [n]           (zeroed)
+  uint32_t* checksum;             // [n]           (zeroed)
+  uint32_t* ticket;               // [4]           (zeroed)
+  unsigned long long* lookback;   // [totalTickets](zeroed)
+  EncEntry* table;                // [n][256]
+  uint8_t* compRows;              // float kinds: [n] rows of compStride bytes
+  uint32_t compStride;
+};
+
+// ---------------------------------------------------------------------------
+// Normalisation epilogue: 256 threads, thread t owns symbol t.
+// Restates ans/GpuANSStatistics.cuh:178-367; the sort is a
+// rank-by-counting over the 256 unique keys (q << 16 | sym), descending.
+// ---------------------------------------------------------------------------
+__device__ void normalizeAndPublish(const uint32_t* __restrict__ histGlobal, uint32_t total,
+                                    int pb, EncEntry* __restrict__ tableOut,
+                                    uint8_t* __restrict__ ansArchive) {
+  __shared__ uint32_t sKey[kNumSymbols];
+  __shared__ uint32_t sQByRank[kNumSymbols];
+  __shared__ uint32_t sSymByRank[kNumSymbols];
+  __shared__ uint32_t sPdf[kNumSymbols];
+  __shared__ uint32_t sWarp[kStatsWarps];
+
+  const uint32_t t = threadIdx.x;
+  const uint32_t K = 1u << pb;
+  const uint32_t count = __ldcg(histGlobal + t);
+
+  // :215-218 fp32 quantisation, IEEE divide, truncation
+  float ratio = __fdiv_rn(__uint2float_rn(count), __uint2float_rn(total));
+  uint32_t q = __float2uint_rz(__fmul_rn((float)K, ratio));
+  if (count > 0 && q == 0) q = 1;
+
+  // sum of q over the block
+  uint32_t incl = q;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) incl += __shfl_xor_sync(0xffffffffu, incl, d);
+  if ((t & 31) == 0) sWarp[t >> 5] = incl;
+  const uint32_t key = (q << 16) | t;
+  sKey[t] = key;
+  __syncthreads();
+  int sum = 0;
+#pragma unroll
+  for (int w = 0; w < kStatsWarps; ++w) sum += (int)sWarp[w];
+
+  // rank = number of keys strictly greater (descending order, keys unique)
+  uint32_t rank = 0;
+#pragma unroll 8
+  for (int j = 0; j < (int)kNumSymbols; ++j) rank += (sKey[j] > key);
+  sQByRank[rank] = q;
+  sSymByRank[rank] = t;
+  __syncthreads();
+
+  // from here thread t owns RANK t
+  uint32_t qr = sQByRank[t];
+  const uint32_t symr = sSymByRank[t];
+  int diff = (int)K - sum;
+  if (diff > 0) {
+    // :258-273: +1 to every entry whose SYMBOL ID < min(diff, 256), repeated
+    while (diff > 0) {
+      int it = diff < (int)kNumSymbols ? diff : (int)kNumSymbols;
+      if ((int)symr < it) qr += 1;
+      diff -= it;
+    }
+  } else if (diff < 0) {
+    // :274-315: -1 from the smallest entries still > 1, by rank, iterated
+    diff = -diff;
+    while (diff > 0) {
+      int g = __syncthreads_count(qr > 1);
+      int it = diff < g ? diff : g;
+      if (it <= 0) break;
+      if ((int)t >= g - it && (int)t < g) qr -= 1;
+      diff -= it;
+    }
+  }
+  sPdf[symr] = qr;
+  __syncthreads();
+
+  // back to thread t == symbol t
+  const uint32_t pdf = sPdf[t];
+  uint32_t totalPdf;
+  const uint32_t cdf = blockExclusiveScan<kStatsThreads>(pdf, sWarp, &totalPdf);
+
+  // :343-358 division constants
+  uint32_t shift = pdf > 1 ? 32u - (uint32_t)__clz((int)(pdf - 1)) : 0u;
+  uint32_t magic = 0;
+  if (pdf > 0) {
+    unsigned long long num = (1ull << 32) * ((1ull << shift) - (unsigned long long)pdf);
+    magic = (uint32_t)(num / pdf + 1ull);
+  }
+  EncEntry e;
+  e.thr = pdf << (31 - pb);
+  e.magic = magic;
+  e.kmpShift = shift | ((K - pdf) << 8);
+  e.cdf = cdf;
+  tableOut[t] = e;
+  // archive: u16 pdf[256] right after the 32 B header (ans/GpuANSEncode.cuh:572-577)
+  reinterpret_cast<uint16_t*>(ansArchive + kAnsHeaderBytes)[t] = (uint16_t)pdf;
+}
+
+// Header + empty pdf for a zero-sized member (ans/ANSTest.cu:243-246 ZeroSized).
+__device__ void publishEmptyMember(uint8_t* ansArchive, int pb, bool useChecksum,
+                                   uint32_t* outSize, uint32_t m, uint32_t extraBytes) {
+  const uint32_t t = threadIdx.x;
+  reinterpret_cast<uint16_t*>(ansArchive + kAnsHeaderBytes)[t] = 0;
+  if (t == 0) {
+    uint4* h = reinterpret_cast<uint4*>(ansArchive);
+    h[0] = make_uint4(kAnsMagicVersion, 0u, 0u, 0u);
+    h[1] = make_uint4((uint32_t)pb | ((useChecksum ? 1u : 0u) << 4), 0u, 0u, 0u);
+    if (outSize) outSize[m] = ansOverhead(0) + extraBytes;
+  }
+}
+
+__device__ __forceinline__ uint32_t foldXor(uint32_t v) {
+  return (v ^ (v >> 8) ^ (v >> 16) ^ (v >> 24)) & 0xffu;
+}
+
+// Adds this CTA's per-warp histograms to the global one, takes the member's
+// completion ticket and tells whether this CTA is the last one.
+__device__ bool flushAndTicket(uint32_t (*sHist)[kNumSymbols], uint32_t* histGlobal,
+                               uint32_t* histDone, uint32_t expected, bool doHist,
+                               uint32_t xorAcc, uint32_t* checksumGlobal, bool doChecksum) {
+  __shared__ uint32_t sLast;
+  __syncthreads();
+  const uint32_t t = threadIdx.x;
+  if (doHist) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < kStatsWarps; ++w) s += sHist[w][t];
+    if (s) atomicAdd(histGlobal + t, s);
+  }
+  if (doChecksum) {
+    uint32_t x = foldXor(xorAcc);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, d);
+    if ((t & 31) == 0 && x) atomicXor(checksumGlobal, x);
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) sLast = (atomicAdd(histDone, 1u) == expected - 1u);
+  __syncthreads();
+  const bool last = sLast != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// ---------------------------------------------------------------------------
+// K1 (bytes): histogram + checksum + normalisation epilogue.
+// grid = (n, Y): CTA (m, y) walks slabs y, y+Y, ... of member m.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStatsThreads)
+statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, int pb,
+                 bool useChecksum, uint32_t slabVecs, uint32_t* __restrict__ outSize) {
+  __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
+  const uint32_t m = blockIdx.x, t = threadIdx.x, warp = t >> 5;
+  const MemberDesc md = sc.members[m];
+  const uint8_t* in = static_cast<const uint8_t*>(md.in);
+  const uint32_t size = md.size;
+  uint8_t* archive = static_cast<uint8_t*>(md.out);
+  const bool doHist = histogramGiven == nullptr;
+  const bool doPass = doHist || useChecksum;
+
+  // member = [head bytes | 16 B vectors | tail bytes]
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15u);
+  const uint32_t head = min(size, (16u - mis) & 15u);
+  const uint32_t nVec = (size - head) / 16u;
+  const uint32_t tail = size - head - nVec * 16u;
+  const uint32_t nSlabs = doPass ? max(divUp(nVec, slabVecs), size > 0 ? 1u : 0u) : 0u;
+  const uint32_t participants = min(nSlabs, gridDim.y);
+
+  if (participants == 0) {
+    if (blockIdx.y != 0) return;
+  } else {
+    if (blockIdx.y >= participants) return;
+#pragma unroll
+    for (int w = 0; w < kStatsWarps; ++w) sHist[w][t] = 0;
+    __syncthreads();
+    uint32_t* wh = sHist[warp];
+    uint32_t xorAcc = 0;
+    if (blockIdx.y == 0) {
+      if (t < head) { uint32_t b = in[t]; atomicAdd(&wh[b], 1u); xorAcc ^= b; }
+      if (t < tail) { uint32_t b = in[head + nVec * 16u + t]; atomicAdd(&wh[b], 1u); xorAcc ^= b; }
+    }
+    const uint4* vec = reinterpret_cast<const uint4*>(in + head);
+    for (uint32_t slab = blockIdx.y; slab < nSlabs; slab += gridDim.y) {
+      const uint32_t v0 = slab * slabVecs, v1 = min(nVec, v0 + slabVecs);
+      for (uint32_t i = v0 + t; i < v1; i += kStatsThreads) {
+        const uint4 v = __ldg(vec + i);
+        xorAcc ^= v.x ^ v.y ^ v.z ^ v.w;
+        if (doHist) {
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            atomicAdd(&wh[w4[k] & 0xffu], 1u);
+            atomicAdd(&wh[(w4[k] >> 8) & 0xffu], 1u);
+            atomicAdd(&wh[(w4[k] >> 16) & 0xffu], 1u);
+            atomicAdd(&wh[w4[k] >> 24], 1u);
+          }
+        }
+      }
+    }
+    if (!flushAndTicket(sHist, sc.hist + m * kNumSymbols, sc.histDone + m, participants, doHist,
+                        xorAcc, sc.checksum + m, useChecksum))
+      return;
+  }
+
+  // ---- last CTA of the member ----
+  if (size == 0) {
+    publishEmptyMember(archive, pb, useChecksum, outSize, m, 0);
+    return;
+  }
+  const uint32_t* h = doHist ? sc.hist + m * kNumSymbols : histogramGiven + m * kNumSymbols;
+  normalizeAndPublish(h, size, pb, sc.table + m * kNumSymbols, archive);
+}
+
+// ---------------------------------------------------------------------------
+// K1 (floats): split + histogram of the comp byte + header + epilogue.
+// float/GpuFloatCompress.cuh:280-365 (splitFloat), float/GpuFloatUtils.cuh:
+// 100-204 (split rules), restated with packed-word bit tricks:
+//   fp16 : comp = w >> 8,            non = w & 0xff
+//   bf16 : w' = rotl16(w, 1); comp = w' >> 8, non = w' & 0xff
+//   fp32 : w' = rotl32(w, 1); comp = w' >> 24, non = w' & 0xffffff
+//          stored as a u16 plane (low 16 bits) then a u8 plane (bits 16..23)
+// ---------------------------------------------------------------------------
+template <int FT>
+__device__ __forceinline__ uint32_t rot16x2(uint32_t w) {
+  if (FT == DGB_BFLOAT16) {
+    // rotate both 16-bit halves left by one
+    return ((w << 1) & 0xfffefffeu) | ((w >> 15) & 0x00010001u);
+  }
+  return w;
+}
+
+template <int FT>
+__global__ void __launch_bounds__(kStatsThreads)
+statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs,
+                 uint32_t* __restrict__ outSize) {
+  __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
+  constexpr uint32_t EPV = (FT == DGB_FLOAT32) ? 4u : 8u;  // elements per 16 B vector
+  constexpr uint32_t WB = (FT == DGB_FLOAT32) ? 4u : 2u;   // word bytes
+  const uint32_t m = blockIdx.x, t = threadIdx.x, warp = t >> 5;
+  const MemberDesc md = sc.members[m];
+  const uint8_t* in = static_cast<const uint8_t*>(md.in);
+  const uint32_t size = md.size;  // float words
+  uint8_t* archive = static_cast<uint8_t*>(md.out);
+  uint8_t* non = archive + kFloatHeaderBytes;
+  const uint32_t nonBytes = floatNonCompBytes(FT, size);
+  uint8_t* ansArchive = non + nonBytes;
+  uint8_t* comp = sc.compRows + (size_t)m * sc.compStride;
+
+  const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+  const uint32_t nVec = aligned ? size / EPV : 0u;
+  const uint32_t nSlabs = size > 0 ? max(divUp(nVec, slabVecs), 1u) : 0u;
+  const uint32_t participants = min(nSlabs, gridDim.y);
+
+  if (participants == 0) {
+    if (blockIdx.y != 0) return;
+  } else {
+    if (blockIdx.y >= participants) return;
+#pragma unroll
+    for (int w = 0; w < kStatsWarps; ++w) sHist[w][t] = 0;
+    __syncthreads();
+    uint32_t* wh = sHist[warp];
+    uint32_t xorAcc = 0;
+
+    // ---- vector body ----
+    const uint4* vec = reinterpret_cast<const uint4*>(in);
+    for (uint32_t slab = blockIdx.y; slab < nSlabs; slab += gridDim.y) {
+      const uint32_t v0 = slab * slabVecs, v1 = min(nVec, v0 + slabVecs);
+      for (uint32_t i = v0 + t; i < v1; i += kStatsThreads) {
+        const uint4 v = __ldg(vec + i);
+        if (FT == DGB_FLOAT32) {
+          const uint32_t r0 = __funnelshift_l(v.x, v.x, 1), r1 = __funnelshift_l(v.y, v.y, 1);
+          const uint32_t r2 = __funnelshift_l(v.z, v.z, 1), r3 = __funnelshift_l(v.w, v.w, 1);
+          // comp = top byte of each rotated word
+          const uint32_t c = __byte_perm(__byte_perm(r0, r1, 0x0073), __byte_perm(r2, r3, 0x0073), 0x5410);
+          reinterpret_cast<uint32_t*>(comp)[i] = c;
+          // u16 plane: low halves
+          uint2 lo;
+          lo.x = __byte_perm(r0, r1, 0x5410);
+          lo.y = __byte_perm(r2, r3, 0x5410);
+          reinterpret_cast<uint2*>(non)[i] = lo;
+          // u8 plane: byte 2 of each
+          const uint32_t hi = __byte_perm(__byte_perm(r0, r1, 0x0062), __byte_perm(r2, r3, 0x0062), 0x5410);
+          reinterpret_cast<uint32_t*>(non + 2u * roundUp(size, 8u))[i] = hi;
+          atomicAdd(&wh[c & 0xffu], 1u);
+          atomicAdd(&wh[(c >> 8) & 0xffu], 1u);
+          atomicAdd(&wh[(c >> 16) & 0xffu], 1u);
+          atomicAdd(&wh[c >> 24], 1u);
+        } else {
+          const uint32_t r0 = rot16x2<FT>(v.x), r1 = rot16x2<FT>(v.y);
+          const uint32_t r2 = rot16x2<FT>(v.z), r3 = rot16x2<FT>(v.w);
+          uint2 c, nn;
+          c.x = __byte_perm(r0, r1, 0x7531);
+          c.y = __byte_perm(r2, r3, 0x7531);
+          nn.x = __byte_perm(r0, r1, 0x6420);
+          nn.y = __byte_perm(r2, r3, 0x6420);
+          reinterpret_cast<uint2*>(comp)[i] = c;
+          reinterpret_cast<uint2*>(non)[i] = nn;
+          atomicAdd(&wh[c.x & 0xffu], 1u);
+          atomicAdd(&wh[(c.x >> 8) & 0xffu], 1u);
+          atomicAdd(&wh[(c.x >> 16) & 0xffu], 1u);
+          atomicAdd(&wh[c.x >> 24], 1u);
+          atomicAdd(&wh[c.y & 0xffu], 1u);
+          atomicAdd(&wh[(c.y >> 8) & 0xffu], 1u);
+          atomicAdd(&wh[(c.y >> 16) & 0xffu], 1u);
+          atomicAdd(&wh[c.y >> 24], 1u);
+        }
+      }
+    }
+    // ---- scalar remainder (and the whole member when not 16 B aligned) ----
+    const uint32_t scalarStart = nVec * EPV;
+    const uint32_t scalarCount = size - scalarStart;
+    if (scalarCount) {
+      // spread the scalar work over the participating CTAs
+      for (uint32_t i = blockIdx.y * kStatsThreads + t; i < scalarCount;
+           i += participants * kStatsThreads) {
+        const uint32_t e = scalarStart + i;
+        uint32_t c;
+        if (FT == DGB_FLOAT32) {
+          uint32_t w = reinterpret_cast<const uint32_t*>(in)[e];
+          w = __funnelshift_l(w, w, 1);
+          c = w >> 24;
+          reinterpret_cast<uint16_t*>(non)[e] = (uint16_t)(w & 0xffffu);
+          (non + 2u * roundUp(size, 8u))[e] = (uint8_t)((w >> 16) & 0xffu);
+        } else {
+          uint32_t w = reinterpret_cast<const uint16_t*>(in)[e];
+          if (FT == DGB_BFLOAT16) w = ((w << 1) | (w >> 15)) & 0xffffu;
+          c = w >> 8;
+          non[e] = (uint8_t)(w & 0xffu);
+        }
+        comp[e] = (uint8_t)c;
+        atomicAdd(&wh[c], 1u);
+      }
+    }
+    if (blockIdx.y == 0) {
+      // float header (float/GpuFloatCompress.cuh:324-337) and zero padding of the planes
+      if (t == 0) {
+        // float-level checksum is patched in by the epilogue CTA
+        *reinterpret_cast<uint4*>(archive) =
+            make_uint4(kFloatMagicVersion, size, (uint32_t)FT | ((useChecksum ? 1u : 0u) << 4), 0u);
+      }
+      if (FT == DGB_FLOAT32) {
+        const uint32_t p16 = 2u * roundUp(size, 8u);
+        for (uint32_t i = 2u * size + t; i < p16; i += kStatsThreads) non[i] = 0;
+        for (uint32_t i = p16 + size + t; i < nonBytes; i += kStatsThreads) non[i] = 0;
+      } else {
+        for (uint32_t i = size + t; i < nonBytes; i += kStatsThreads) non[i] = 0;
+      }
+    }
+    if (useChecksum) {
+      // the float checksum covers the first `size` BYTES only
+      const uint32_t cbytes = size;  // bytes, not words
+      for (uint32_t i = blockIdx.y * kStatsThreads + t; i < cbytes; i += participants * kStatsThreads)
+        xorAcc ^= in[i];
+    }
+    (void)WB;
+    if (!flushAndTicket(sHist, sc.hist + m * kNumSymbols, sc.histDone + m, participants, true,
+                        xorAcc, sc.checksum + m, useChecksum))
+      return;
+  }
+
+  // ---- last CTA of the member ----
+  if (size == 0) {
+    if (t == 0) {
+      *reinterpret_cast<uint4*>(archive) =
+          make_uint4(kFloatMagicVersion, 0u, (uint32_t)FT | ((useChecksum ? 1u : 0u) << 4), 0u);
+    }
+    publishEmptyMember(ansArchive, pb, false, outSize, m, kFloatHeaderBytes + nonBytes);
+    return;
+  }
+  if (useChecksum && t == 0) {
+    reinterpret_cast<uint32_t*>(archive)[3] = __ldcg(sc.checksum + m);
+  }
+  normalizeAndPublish(sc.hist + m * kNumSymbols, size, pb, sc.table + m * kNumSymbols, ansArchive);
+}
+
+// ---------------------------------------------------------------------------
+// K2: the rANS state machine + single-pass packing.
+// ---------------------------------------------------------------------------
+
+// One rANS step for a full row (ans/GpuANSEncode.cuh:49-90 restated).  The
+// update uses x' = (x / pdf) * (2^pb - pdf) + x + cdf, which equals
+// (x / pdf) << pb + x % pdf + cdf, so the loop needs neither pdf nor pb.
+// `wa` is the shared-memory BYTE address of the next free staging word.
+__device__ __forceinline__ void stsU16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+
+__device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t sym,
+                                           const EncEntry* __restrict__ tab, uint32_t& wa,
+                                           uint32_t ltMask) {
+  const EncEntry e = tab[sym];
+  const bool wr = state >= e.thr;
+  const uint32_t vote = __ballot_sync(0xffffffffu, wr);
+  if (wr) {
+    stsU16(wa + 2u * __popc(vote & ltMask), state);
+    state >>= 16;
+  }
+  wa += 2u * __popc(vote);
+  const uint32_t tq = __umulhi(state, e.magic);
+  const uint32_t div = __funnelshift_r(tq + state, 0u, e.kmpShift);  // shift = kmpShift & 31
+  state = div * (e.kmpShift >> 8) + state + e.cdf;
+}
+
+__device__ __forceinline__ void encodeStepPartial(bool valid, uint32_t& state, uint32_t sym,
+                                                  const EncEntry* __restrict__ tab, uint32_t& wa,
+                                                  uint32_t ltMask) {
+  const EncEntry e = tab[sym];
+  const bool wr = valid && state >= e.thr;
+  const uint32_t vote = __ballot_sync(0xffffffffu, wr);
+  if (wr) {
+    stsU16(wa + 2u * __popc(vote & ltMask), state);
+    state >>= 16;
+  }
+  wa += 2u * __popc(vote);
+  const uint32_t tq = __umulhi(state, e.magic);
+  const uint32_t div = __funnelshift_r(tq + state, 0u, e.kmpShift);
+  const uint32_t next = div * (e.kmpShift >> 8) + state + e.cdf;
+  state = valid ? next : state;
+}
+
+// Encodes bytes [0, n) of one block with one warp into the staging slot at
+// shared byte address `stageAddr`.  Returns the word count.
+__device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ in, uint32_t n,
+                                                    const EncEntry* __restrict__ tab,
+                                                    uint32_t stageAddr, uint32_t lane,
+                                                    uint32_t& stateOut) {
+  uint32_t state = kStateMin;
+  uint32_t wa = stageAddr;
+  const uint32_t ltMask = laneMaskLt();
+  const uint32_t fullRows = n >> 5;
+  const uint8_t* p = in + lane;
+  uint32_t r = 0;
+  constexpr int U = 8;
+  for (; r + U <= fullRows; r += U, p += U * 32) {
+    uint32_t sym[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) sym[j] = p[j * 32];
+#pragma unroll
+    for (int j = 0; j < U; ++j) encodeStep(state, sym[j], tab, wa, ltMask);
+  }
+  for (; r < fullRows; ++r, p += 32) encodeStep(state, p[0], tab, wa, ltMask);
+  const uint32_t rem = n & 31u;
+  if (rem) {
+    const bool valid = lane < rem;
+    const uint32_t sym = valid ? p[0] : 0u;
+    encodeStepPartial(valid, state, sym, tab, wa, ltMask);
+  }
+  stateOut = state;
+  return (wa - stageAddr) >> 1;
+}
+
+constexpr unsigned long long kFlagAgg = 1ull << 32;
+constexpr unsigned long long kFlagPrefix = 2ull << 32;
+
+// Exclusive prefix of the per-ticket totals of this member (decoupled
+// look-back, one warp).  first = first ticket of the member.
+__device__ __forceinline__ uint32_t lookbackWarp(volatile unsigned long long* desc, uint32_t ticket,
+                                                 uint32_t first, uint32_t lane) {
+  uint32_t base = 0;
+  int64_t idx = (int64_t)ticket - 1;
+  while (idx >= (int64_t)first) {
+    const int64_t mine = idx - lane;
+    unsigned long long d = kFlagPrefix;  // lanes before `first`: neutral, terminates the walk
+    if (mine >= (int64_t)first) {
+      do { d = desc[mine]; } while ((d >> 32) == 0ull);
+    }
+    const bool isPrefix = (d >> 32) == 2ull;
+    const uint32_t pmask = __ballot_sync(0xffffffffu, isPrefix);
+    // lanes 0..firstPrefixLane contribute (lane 0 is the nearest predecessor)
+    const uint32_t stop = pmask ? (uint32_t)__ffs((int)pmask) - 1u : 31u;
+    uint32_t v = lane <= stop ? (uint32_t)d : 0u;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    base += v;
+    if (pmask) break;
+    idx -= 32;
+  }
+  return base;
+}
+
+__global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksum,
+                             uint32_t numMembers, uint32_t totalTickets, int warpsPerCta,
+                             uint32_t* __restrict__ outSize) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ EncEntry sTab[kNumSymbols];  // static: constant base address for the hot LDS.128
+  __shared__ uint32_t sWords[32];         // [warps] padded word counts
+  __shared__ uint32_t sMisc[4];           // ticket, member, base, total
+  const uint32_t slotWords = maxBlockWords(pb);
+  uint16_t* sStage = reinterpret_cast<uint16_t*>(smem);
+
+  const uint32_t t = threadIdx.x, lane = t & 31u;
+  // shuffle => provably warp-uniform (no divergence check around the votes in the hot loop)
+  const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const uint32_t W = (uint32_t)warpsPerCta;
+  uint16_t* myStage = sStage + (size_t)warp * slotWords;
+  volatile unsigned long long* desc = sc.lookback;
+  uint32_t curMember = 0xffffffffu;
+
+  for (;;) {
+    __syncthreads();  // previous iteration's staging / sMisc fully consumed
+    if (t == 0) {
+      const uint32_t tk = atomicAdd(sc.ticket, 1u);
+      sMisc[0] = tk;
+      if (tk < totalTickets) {
+        // member m with work0[m] <= tk < work0[m+1]  (binary search, L1-cached)
+        uint32_t lo = 0, hi = numMembers;
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (__ldg(&sc.members[mid].work0) <= tk) lo = mid; else hi = mid;
+        }
+        sMisc[1] = lo;
+      }
+    }
+    __syncthreads();
+    const uint32_t ticket = sMisc[0];
+    if (ticket >= totalTickets) break;
+    const uint32_t m = sMisc[1];
+    const MemberDesc md = sc.members[m];
+    const uint32_t size = md.size;
+    const uint32_t nb = divUp(size, kBlockBytes);
+    const uint32_t chunk = ticket - md.work0;
+    const uint32_t numChunks = divUp(nb, W);
+
+    const uint8_t* ansIn;
+    uint8_t* ansOut;
+    uint32_t extraBytes = 0;
+    if (kind == kKindBytes) {
+      ansIn = static_cast<const uint8_t*>(md.in);
+      ansOut = static_cast<uint8_t*>(md.out);
+    } else {
+      ansIn = sc.compRows + (size_t)m * sc.compStride;
+      extraBytes = kFloatHeaderBytes + floatNonCompBytes(kind, size);
+      ansOut = static_cast<uint8_t*>(md.out) + extraBytes;
+    }
+    __builtin_assume(__isGlobal(ansIn));
+    __builtin_assume(__isGlobal(ansOut));
+
+    if (m != curMember) {
+      // encoder table of this member -> shared memory (written by K1's epilogue)
+      const uint4* src = reinterpret_cast<const uint4*>(sc.table + (size_t)m * kNumSymbols);
+      for (uint32_t i = t; i < kNumSymbols; i += blockDim.x)
+        reinterpret_cast<uint4*>(sTab)[i] = __ldcg(src + i);
+      curMember = m;
+      __syncthreads();
+    }
+
+    // ---- each warp encodes one block into its staging slot ----
+    const uint32_t block = chunk * W + warp;
+    uint32_t words = 0, padded = 0, state = kStateMin, blockLen = 0;
+    if (block < nb) {
+      const uint32_t start = block * kBlockBytes;
+      blockLen = min(kBlockBytes, size - start);
+      words = encodeBlockWarp(ansIn + start, blockLen, sTab, smemAddr(myStage), lane, state);
+      padded = roundUp(words, 8u);
+      if (words + lane < padded) myStage[words + lane] = 0;  // pad < 8 words
+    }
+    if (lane == 0) sWords[warp] = padded;
+    __syncthreads();
+
+    // ---- ticket total, look-back (warp 0), broadcast of the base offset ----
+    if (warp == 0) {
+      uint32_t v = lane < W ? sWords[lane] : 0u;
+      uint32_t tot = v;
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
+      uint32_t base = 0;
+      if (chunk != 0) {
+        if (lane == 0) desc[ticket] = kFlagAgg | tot;
+        base = lookbackWarp(desc, ticket, md.work0, lane);
+      }
+      if (lane == 0) {
+        desc[ticket] = kFlagPrefix | (unsigned long long)(base + tot);
+        sMisc[2] = base;
+        sMisc[3] = tot;
+      }
+    }
+    __syncthreads();
+    uint32_t myOff = sMisc[2];
+    for (uint32_t w = 0; w < warp; ++w) myOff += sWords[w];
+
+    // ---- final placement: states, blockWords, packed stream ----
+    uint8_t* pStates = ansOut + kAnsHeaderBytes + kAnsPdfBytes;
+    uint8_t* pBlockWords = pStates + 128u * nb;
+    uint8_t* pData = pBlockWords + 8u * roundUp(nb, 2u);
+    if (block < nb) {
+      reinterpret_cast<uint32_t*>(pStates)[block * 32u + lane] = state;
+      if (lane == 0)
+        reinterpret_cast<uint2*>(pBlockWords)[block] = make_uint2((blockLen << 16) | words, myOff);
+      uint4* dst = reinterpret_cast<uint4*>(pData + 2u * (size_t)myOff);
+      const uint4* src = reinterpret_cast<const uint4*>(myStage);
+      for (uint32_t i = lane; i < padded / 8u; i += 32u) dst[i] = src[i];
+    }
+    if (chunk == numChunks - 1 && t == 0) {
+      // ans/GpuANSEncode.cuh:553-569 header (undefined bits zeroed)
+      const uint32_t totalWords = sMisc[2] + sMisc[3];
+      uint4* h = reinterpret_cast<uint4*>(ansOut);
+      h[0] = make_uint4(kAnsMagicVersion, nb, size, totalWords);
+      const bool ansChecksum = useChecksum && kind == kKindBytes;
+      h[1] = make_uint4((uint32_t)pb | ((ansChecksum ? 1u : 0u) << 4),
+                        ansChecksum ? __ldcg(sc.checksum + m) : 0u, 0u, 0u);
+      if (nb & 1u) reinterpret_cast<uint2*>(pBlockWords)[nb] = make_uint2(0u, 0u);
+      if (outSize) outSize[m] = ansOverhead(nb) + 2u * totalWords + extraBytes;
+    }
+  }
+}
+
+size_t alignUp256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct ScratchPlan {
+  size_t members, zeroBegin, hist, histDone, checksum, ticket, lookback, zeroEnd, table, compRows, total;
+  uint32_t compStride;
+};
+
+ScratchPlan planScratch(int kind, uint32_t n, uint32_t maxSize, uint32_t totalTickets) {
+  ScratchPlan p{};
+  size_t o = 0;
+  p.members = o; o = alignUp256(o + sizeof(MemberDesc) * (size_t)n);
+  p.zeroBegin = o;
+  p.hist = o; o = alignUp256(o + sizeof(uint32_t) * kNumSymbols * (size_t)n);
+  p.histDone = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
+  p.checksum = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
+  p.ticket = o; o = alignUp256(o + 16);
+  p.lookback = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)totalTickets);
+  p.zeroEnd = o;
+  p.table = o; o = alignUp256(o + sizeof(EncEntry) * kNumSymbols * (size_t)n);
+  p.compStride = kind == kKindBytes ? 0u : roundUp(maxSize, 16u);
+  p.compRows = o; o = alignUp256(o + (size_t)p.compStride * n);
+  p.total = o;
+  return p;
+}
+
+int smCount() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+
+uint32_t ticketsFor(uint32_t size, uint32_t W) { return divUp(divUp(size, kBlockBytes), W); }
+
+}  // namespace
+
+size_t encodeTempBytes(int kind, uint32_t n, uint32_t maxSize) {
+  // worst case over warps-per-CTA choices: tickets with W = 1
+  const uint64_t tickets = (uint64_t)n * divUp(maxSize, kBlockBytes);
+  if (tickets > 0xffffffffull) return ~size_t(0);
+  return planScratch(kind, n, maxSize, (uint32_t)tickets).total + 256;
+}
+
+int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, uint32_t n,
+                const HostMember* members, const uint32_t* histogram_dev, uint32_t* outSize_dev,
+                cudaStream_t stream) {
+  if (n == 0) return DGB_OK;
+  if (pb < 9 || pb > 11) return DGB_ERR_INVALID_ARG;
+  if (kind != kKindBytes && histogram_dev) return DGB_ERR_INVALID_ARG;
+  const Options& opt = options();
+  const uint32_t W = (uint32_t)std::max(1, std::min(opt.encode_warps, 16));
+
+  std::vector<MemberDesc> desc(n);
+  uint32_t maxSize = 0;
+  uint64_t tickets = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const HostMember& hm = members[i];
+    if ((hm.size && !hm.in) || !hm.out) return DGB_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(hm.out) & 15u) return DGB_ERR_INVALID_ARG;
+    const uint32_t wordBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
+    if (reinterpret_cast<uintptr_t>(hm.in) & (wordBytes - 1u)) return DGB_ERR_INVALID_ARG;
+    desc[i].in = hm.in;
+    desc[i].out = hm.out;
+    desc[i].size = hm.size;
+    desc[i].work0 = (uint32_t)tickets;
+    tickets += ticketsFor(hm.size, W);
+    maxSize = std::max(maxSize, hm.size);
+    if (tickets > 0x7fffffffull) return DGB_ERR_TOO_LARGE;
+  }
+  const uint32_t totalTickets = (uint32_t)tickets;
+  const ScratchPlan sp = planScratch(kind, n, maxSize, totalTickets);
+  if (!temp || tempBytes < sp.total || (reinterpret_cast<uintptr_t>(temp) & 255u))
+    return temp && tempBytes >= sp.total ? DGB_ERR_INVALID_ARG : DGB_ERR_TEMP_TOO_SMALL;
+
+  uint8_t* base = static_cast<uint8_t*>(temp);
+  EncodeScratch sc;
+  sc.members = reinterpret_cast<MemberDesc*>(base + sp.members);
+  sc.hist = reinterpret_cast<uint32_t*>(base + sp.hist);
+  sc.histDone = reinterpret_cast<uint32_t*>(base + sp.histDone);
+  sc.checksum = reinterpret_cast<uint32_t*>(base + sp.checksum);
+  sc.ticket = reinterpret_cast<uint32_t*>(base + sp.ticket);
+  sc.lookback = reinterpret_cast<unsigned long long*>(base + sp.lookback);
+  sc.table = reinterpret_cast<EncEntry*>(base + sp.table);
+  sc.compRows = base + sp.compRows;
+  sc.compStride = sp.compStride;
+
+  DGB_CUDA_TRY(cudaMemcpyAsync(sc.members, desc.data(), sizeof(MemberDesc) * n,
+                               cudaMemcpyHostToDevice, stream));
+  DGB_CUDA_TRY(cudaMemsetAsync(base + sp.zeroBegin, 0, sp.zeroEnd - sp.zeroBegin, stream));
+
+  // ---- K1 ----
+  const int sms = smCount();
+  const uint32_t elemBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
+  const uint32_t slabVecs = std::max(1, opt.hist_slab_kb) * 1024u / 16u;
+  const uint64_t maxVecs = ((uint64_t)maxSize * elemBytes) / 16u;
+  uint32_t gridY = (uint32_t)std::max<uint64_t>(1, (maxVecs + slabVecs - 1) / slabVecs);
+  // enough CTAs to fill the machine a few times, never more than the slabs
+  const uint32_t wantY = std::max(1u, (uint32_t)(8 * sms * 4) / n);
+  gridY = std::min(std::min(gridY, wantY), 65535u);
+  dim3 grid1(n, gridY);
+  if (kind == kKindBytes) {
+    statsBytesKernel<<<grid1, kStatsThreads, 0, stream>>>(sc, histogram_dev, pb, checksum, slabVecs,
+                                                          outSize_dev);
+  } else if (kind == kKindF16) {
+    statsFloatKernel<DGB_FLOAT16><<<grid1, kStatsThreads, 0, stream>>>(sc, pb, checksum, slabVecs, outSize_dev);
+  } else if (kind == kKindBF16) {
+    statsFloatKernel<DGB_BFLOAT16><<<grid1, kStatsThreads, 0, stream>>>(sc, pb, checksum, slabVecs, outSize_dev);
+  } else {
+    statsFloatKernel<DGB_FLOAT32><<<grid1, kStatsThreads, 0, stream>>>(sc, pb, checksum, slabVecs, outSize_dev);
+  }
+  DGB_CUDA_TRY(cudaGetLastError());
+
+  // ---- K2 ----
+  if (totalTickets > 0) {
+    const size_t smemBytes = (size_t)W * maxBlockWords(pb) * 2;
+    static bool configured = false;
+    if (!configured) {
+      DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(200 * 1024)));
+      configured = true;
+    }
+    static size_t occKeySmem = 0;
+    static uint32_t occKeyW = 0;
+    static int perSm = 1;
+    if (occKeySmem != smemBytes || occKeyW != W) {
+      int occ = 0;
+      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel, (int)(W * 32),
+                                                                 smemBytes));
+      perSm = std::max(occ, 1);
+      occKeySmem = smemBytes;
+      occKeyW = W;
+    }
+    const uint32_t grid2 = std::min<uint32_t>(totalTickets, (uint32_t)(perSm * sms));
+    encodeKernel<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, (int)W,
+                                                      outSize_dev);
+    DGB_CUDA_TRY(cudaGetLastError());
+  }
+  return DGB_OK;
+}
+
+}  // namespace dgb

@@ -1,0 +1,362 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via dietgpu_b200.ops) against the CPU oracle.
+Bit-exact everywhere: archives must equal the oracle's byte for byte (the encoder zeroes the bits
+the reference leaves undefined, as the oracle does), decode must reproduce the input."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import exp_bytes, normal_words, zipf_bytes
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {"f16": (O.F16, torch.float16, np.uint16), "bf16": (O.BF16, torch.bfloat16, np.uint16),
+         "f32": (O.F32, torch.float32, np.uint32)}
+
+
+def dg():
+    import dietgpu_b200
+
+    return dietgpu_b200
+
+
+def to_dev_bytes(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def words_to_tensor(w, kind):
+    _, tdt, _ = KINDS[kind]
+    t = torch.from_numpy(w.view(np.int16 if w.dtype == np.uint16 else np.int32).copy())
+    return t.view(tdt).cuda()
+
+
+def ans_roundtrip(arrays, pb, checksum=False):
+    ts = [to_dev_bytes(a) for a in arrays]
+    comp, sizes, _ = dg().compress_data(False, ts, checksum, prob_bits=pb)
+    hs = sizes.cpu().tolist()
+    rows = []
+    for i, a in enumerate(arrays):
+        want = O.ans_encode(a, pb, checksum)
+        got = comp[i, :hs[i]].cpu().numpy()
+        assert hs[i] == want.size, f"member {i}: size {hs[i]} != oracle {want.size}"
+        assert hs[i] % 16 == 0  # ans/ANSTest.cu:131-135
+        assert np.array_equal(got, want), f"member {i}: archive bytes differ from oracle"
+        rows.append(comp[i, :hs[i]].clone())  # exactly-truncated buffers (ans_test.py:21-26)
+    outs = [torch.empty_like(t) for t in ts]
+    status = torch.zeros(len(ts), dtype=torch.uint8, device="cuda")
+    osz = torch.zeros(len(ts), dtype=torch.int32, device="cuda")
+    dg().decompress_data(False, rows, outs, checksum, None, status, osz, prob_bits=pb)
+    assert status.cpu().tolist() == [1] * len(ts)
+    assert osz.cpu().tolist() == [a.size for a in arrays]
+    for t, o in zip(ts, outs):
+        assert torch.equal(t, o)
+
+
+@pytest.mark.parametrize("pb", [9, 10, 11])
+@pytest.mark.parametrize("lam", [1.0, 10.0, 100.0, 1000.0])
+def test_ans_batch_pointer(pb, lam):
+    # size lists of ans/ANSTest.cu:248-260 (BatchPointer), checksum on as there (:121)
+    for sizes in ([1], [1, 1], [4096, 4095, 4096], [1234, 2345, 3456], [10000, 10013, 10000]):
+        arrays = [exp_bytes(n, lam, 10 + i) for i, n in enumerate(sizes)]
+        ans_roundtrip(arrays, pb, checksum=True)
+
+
+def test_ans_zero_sized():
+    # ans/ANSTest.cu:243-246 ZeroSized, alone and inside a batch
+    ans_roundtrip([np.zeros(0, np.uint8)], 10)
+    ans_roundtrip([exp_bytes(5000, 20, 1), np.zeros(0, np.uint8), exp_bytes(77, 5, 2)], 10, checksum=True)
+
+
+def test_ans_batch_large():
+    # ans/ANSTest.cu:262-275 BatchPointerLarge: 100 members of 100..10000 bytes
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(100, 10000, 100)
+    ans_roundtrip([exp_bytes(int(n), 20.0, 100 + i) for i, n in enumerate(sizes)], 10)
+
+
+def test_ans_block_boundaries_and_distributions():
+    arrays = []
+    for n in (31, 32, 33, 4064, 4095, 4096, 4097, 8191, 8192, 8193, 65536 + 17):
+        arrays.append(zipf_bytes(n, 1.0, n))
+    arrays.append(np.full(10000, 7, np.uint8))                      # single symbol: pdf == 2^pb
+    arrays.append(np.random.default_rng(5).integers(0, 256, 50000, dtype=np.uint8))  # incompressible
+    arrays.append((np.random.default_rng(6).integers(100, 160, 30000)).astype(np.uint8))
+    for pb in (9, 10, 11):
+        ans_roundtrip(arrays, pb)
+
+
+def test_ans_config1_uniform_1mib():
+    # BASELINE configs[0]: 1 MiB uniform random bytes, batch 1, prec 10
+    a = np.random.default_rng(1234).integers(0, 256, 1 << 20, dtype=np.uint8)
+    ans_roundtrip([a], 10)
+
+
+def test_ans_unaligned_inputs():
+    # inputs need only 4 B alignment (ans/GpuANSCodec.h:16); exercise odd offsets too
+    base = to_dev_bytes(zipf_bytes(40000, 1.2, 9))
+    for off in (0, 1, 3, 4, 12, 20):
+        t = base[off:off + 20000]
+        comp, sizes, _ = dg().compress_data(False, [t])
+        n = int(sizes[0])
+        want = O.ans_encode(t.cpu().numpy(), 10)
+        assert n == want.size and np.array_equal(comp[0, :n].cpu().numpy(), want)
+        out = torch.empty(20000 + 8, dtype=torch.uint8, device="cuda")[off % 8:][:20000]
+        dg().decompress_data(False, [comp[0, :n]], [out])
+        assert torch.equal(out, t)
+
+
+def test_ans_decode_oracle_archives():
+    # archives produced by the oracle (== reference format) decode bit-exactly
+    arrays = [exp_bytes(12345, 30, 1), zipf_bytes(70000, 1.5, 2), exp_bytes(1, 1, 3)]
+    for pb in (9, 10, 11):
+        rows = [to_dev_bytes(O.ans_encode(a, pb)) for a in arrays]
+        outs = [torch.empty(a.size, dtype=torch.uint8, device="cuda") for a in arrays]
+        dg().decompress_data(False, rows, outs, prob_bits=pb)
+        for a, o in zip(arrays, outs):
+            assert np.array_equal(o.cpu().numpy(), a)
+
+
+def test_ans_capacity_and_bad_header():
+    a = exp_bytes(10000, 20, 1)
+    row = to_dev_bytes(O.ans_encode(a, 10))
+    bad = row.clone()
+    bad[0] = 0  # break the magic
+    outs = [torch.zeros(9999, dtype=torch.uint8, device="cuda"), torch.zeros(10000, dtype=torch.uint8, device="cuda"),
+            torch.zeros(10000, dtype=torch.uint8, device="cuda")]
+    status = torch.full((3,), 9, dtype=torch.uint8, device="cuda")
+    osz = torch.zeros(3, dtype=torch.int32, device="cuda")
+    dg().decompress_data(False, [row, row, bad], outs, False, None, status, osz)
+    # ans/GpuANSDecode.cuh:326-341: too-small capacity -> success 0, size = required; member skipped
+    assert status.cpu().tolist() == [0, 1, 0]
+    assert osz.cpu().tolist() == [10000, 10000, 0]
+    assert int(outs[0].sum()) == 0 and int(outs[2].sum()) == 0
+    assert np.array_equal(outs[1].cpu().numpy(), a)
+    # wrong precision is rejected per member rather than asserted
+    status.fill_(9)
+    dg().decompress_data(False, [row], [outs[1]], False, None, status[:1], osz[:1], prob_bits=11)
+    assert int(status[0]) == 0
+
+
+def test_ans_checksum_mismatch_detected():
+    a = exp_bytes(20000, 20, 1)
+    arch = O.ans_encode(a, 10, True)
+    arch[20] ^= 0x5A  # stored checksum field
+    out = torch.empty(a.size, dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="checksum mismatch"):
+        dg().decompress_data(False, [to_dev_bytes(arch)], [out], True)
+
+
+def test_ans_split_size_api():
+    # ans_test.py:100-139 split-size compress / decompress
+    sizes = [4096, 8000, 12, 20000, 5]  # interior sizes multiples of 4
+    arrays = [exp_bytes(n, 15, 40 + i) for i, n in enumerate(sizes)]
+    flat = to_dev_bytes(np.concatenate(arrays))
+    splits = torch.tensor(sizes, dtype=torch.int32)
+    rows, csz, _ = dg().compress_data_split_size(False, flat, splits, True)
+    for i, a in enumerate(arrays):
+        assert np.array_equal(rows[i].cpu().numpy(), O.ans_encode(a, 10, True))
+    out = torch.empty_like(flat)
+    status = torch.zeros(len(sizes), dtype=torch.uint8, device="cuda")
+    dg().decompress_data_split_size(False, rows, out, splits, True, None, status, None)
+    assert status.cpu().tolist() == [1] * len(sizes)
+    assert torch.equal(out, flat)
+
+
+def test_ans_stride_api():
+    # ans/ANSTest.cu:277-282 BatchStride: 13 members of 8208 bytes
+    import ctypes as C
+
+    from dietgpu_b200 import capi
+
+    n, size = 13, 8208
+    stride_in = 8208 + 48
+    arrays = [exp_bytes(size, 25, 60 + i) for i in range(n)]
+    buf = torch.zeros(n * stride_in, dtype=torch.uint8, device="cuda")
+    for i, a in enumerate(arrays):
+        buf[i * stride_in:i * stride_in + size] = to_dev_bytes(a)
+    L = capi.lib()
+    ostride = L.dgb_ans_max_compressed_size(size)
+    comp = torch.zeros(n * ostride, dtype=torch.uint8, device="cuda")
+    csz = torch.zeros(n, dtype=torch.int32, device="cuda")
+    tb = L.dgb_ans_encode_temp_bytes(n, size)
+    temp = torch.empty(tb + 256, dtype=torch.uint8, device="cuda")
+    tp = temp.data_ptr() + (-temp.data_ptr()) % 256
+    st = torch.cuda.current_stream().cuda_stream
+    capi.check(L.dgb_ans_encode_stride(tp, tb, 10, 1, n, buf.data_ptr(), size, stride_in, None,
+                                       comp.data_ptr(), ostride, csz.data_ptr(), st), "encode_stride")
+    hs = csz.cpu().tolist()
+    for i, a in enumerate(arrays):
+        assert np.array_equal(comp[i * ostride:i * ostride + hs[i]].cpu().numpy(), O.ans_encode(a, 10, True))
+    out = torch.zeros(n * stride_in, dtype=torch.uint8, device="cuda")
+    status = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mism = (C.c_uint8 * n)()
+    capi.check(L.dgb_ans_decode_stride(tp, tb, 10, 1, n, comp.data_ptr(), ostride, out.data_ptr(), stride_in,
+                                       size, status.data_ptr(), None, mism, st), "decode_stride")
+    assert status.cpu().tolist() == [1] * n and list(mism) == [0] * n
+    assert torch.equal(out, buf)
+
+
+# ------------------------------------------------------------------ floats ----
+
+def float_roundtrip(kind, word_arrays, pb=10, checksum=False, offsets=None):
+    ft, tdt, _ = KINDS[kind]
+    ts = []
+    for i, w in enumerate(word_arrays):
+        off = 0 if offsets is None else offsets[i]
+        full = words_to_tensor(np.concatenate([np.zeros(off, w.dtype), w]), kind)
+        ts.append(full[off:])  # element-aligned but possibly not 16 B aligned (float/FloatTest.cu:276-282)
+    comp, sizes, _ = dg().compress_data(True, ts, checksum, prob_bits=pb)
+    hs = sizes.cpu().tolist()
+    rows = []
+    for i, w in enumerate(word_arrays):
+        want = O.float_compress(ft, w, pb, checksum)
+        assert hs[i] == want.size, f"member {i}: size {hs[i]} != oracle {want.size}"
+        assert np.array_equal(comp[i, :hs[i]].cpu().numpy(), want), f"member {i}: archive differs"
+        rows.append(comp[i, :hs[i]].clone())
+    outs = []
+    for i, t in enumerate(ts):
+        off = 0 if offsets is None else (offsets[i] + 1) % 5
+        outs.append(torch.empty(t.numel() + off, dtype=tdt, device="cuda")[off:])
+    status = torch.zeros(len(ts), dtype=torch.uint8, device="cuda")
+    osz = torch.zeros(len(ts), dtype=torch.int32, device="cuda")
+    dg().decompress_data(True, rows, outs, checksum, None, status, osz, prob_bits=pb)
+    assert status.cpu().tolist() == [1] * len(ts)
+    assert osz.cpu().tolist() == [w.size for w in word_arrays]
+    it = torch.int16 if kind != "f32" else torch.int32
+    for t, o in zip(ts, outs):
+        assert torch.equal(t.view(it), o.view(it))
+
+
+@pytest.mark.parametrize("kind", ["f16", "bf16", "f32"])
+@pytest.mark.parametrize("pb", [9, 10])
+def test_float_batch(kind, pb):
+    # float/FloatTest.cu:270-311: B in {1,3,16,23}, sizes 1..10000, with and without 16 B alignment
+    rng = np.random.default_rng(11)
+    for b in (1, 3, 16, 23):
+        sizes = [int(x) for x in rng.integers(1, 10000, b)]
+        arrs = [normal_words(n, kind, 10 + n) for n in sizes]
+        float_roundtrip(kind, arrs, pb, checksum=True)
+        float_roundtrip(kind, arrs, pb, offsets=[int(x) for x in rng.integers(0, 9, b)])
+
+
+@pytest.mark.parametrize("kind", ["f16", "bf16", "f32"])
+def test_float_large_batch_and_sizes(kind):
+    # FloatTest LargeBatch (B = 256 > the reference's inline-parameter limit) and a 512 Ki member
+    arrs = [normal_words(1000 + 7 * i, kind, i) for i in range(256)]
+    float_roundtrip(kind, arrs, 10)
+    float_roundtrip(kind, [normal_words(512 * 1024, kind, 5), normal_words(0, kind, 6), normal_words(1, kind, 7)], 10, checksum=True)
+
+
+@pytest.mark.parametrize("kind", ["f16", "bf16"])
+def test_float_relu_sparse(kind):
+    # BASELINE configs[3] shape: ~50 % exact zeros
+    float_roundtrip(kind, [normal_words(300000, kind, 3, relu=True) for _ in range(3)], 10)
+
+
+def test_float_simple_api_shrinks():
+    # float_test.py:50-92: compress_data_simple must actually shrink N(0,1) data
+    for kind in ("bf16", "f16", "f32"):
+        _, tdt, _ = KINDS[kind]
+        ts = [words_to_tensor(normal_words(n, kind, n), kind) for n in (10000, 100000, 1000000)]
+        comp = dg().compress_data_simple(True, ts, True)
+        for t, c in zip(ts, comp):
+            assert c.numel() < t.numel() * t.element_size()
+        outs = dg().decompress_data_simple(True, comp, True)
+        it = torch.int16 if kind != "f32" else torch.int32
+        for t, o in zip(ts, outs):
+            assert o.dtype == tdt and torch.equal(t.view(it), o.view(it))
+
+
+def test_float_split_size_api():
+    # float_test.py:94-178 split-size with and without 16 B alignment
+    for kind in ("bf16", "f16", "f32"):
+        sizes = [4096, 12345, 7, 100000]
+        arrs = [normal_words(n, kind, 70 + i) for i, n in enumerate(sizes)]
+        flat = words_to_tensor(np.concatenate(arrs), kind)
+        splits = torch.tensor(sizes, dtype=torch.int32)
+        rows, _, _ = dg().compress_data_split_size(True, flat, splits, True)
+        ft = KINDS[kind][0]
+        for r, a in zip(rows, arrs):
+            assert np.array_equal(r.cpu().numpy(), O.float_compress(ft, a, 10, True))
+        out = torch.empty_like(flat)
+        dg().decompress_data_split_size(True, rows, out, splits, True)
+        it = torch.int16 if kind != "f32" else torch.int32
+        assert torch.equal(out.view(it), flat.view(it))
+
+
+def test_float_capacity_failure():
+    w = normal_words(5000, "bf16", 1)
+    row = to_dev_bytes(O.float_compress(O.BF16, w, 10))
+    outs = [torch.zeros(4999, dtype=torch.bfloat16, device="cuda"), torch.zeros(5000, dtype=torch.bfloat16, device="cuda")]
+    status = torch.full((2,), 9, dtype=torch.uint8, device="cuda")
+    osz = torch.zeros(2, dtype=torch.int32, device="cuda")
+    dg().decompress_data(True, [row, row], outs, False, None, status, osz)
+    assert status.cpu().tolist() == [0, 1] and osz.cpu().tolist() == [5000, 5000]
+    assert np.array_equal(outs[1].view(torch.int16).cpu().numpy().view(np.uint16), w)
+
+
+# ------------------------------------------- full-size configs (properties) ----
+
+def test_config2_zipf_256mib_roundtrip():
+    # BASELINE configs[1]: 64 x 4 MiB Zipf bytes, prec 10 and 11: round trip + size == oracle on a sample
+    members = [to_dev_bytes(zipf_bytes(4 << 20, 1.0 if i % 2 == 0 else 1.5, 1234 + i)) for i in range(8)]
+    ts = [members[i % 8] for i in range(64)]
+    for pb in (10, 11):
+        comp, sizes, _ = dg().compress_data(False, ts, prob_bits=pb)
+        hs = sizes.cpu().tolist()
+        for i in (0, 1):
+            want = O.ans_encode(members[i].cpu().numpy(), pb)
+            assert hs[i] == want.size and np.array_equal(comp[i, :hs[i]].cpu().numpy(), want)
+        assert hs[:8] * 8 == hs
+        outs = [torch.empty_like(t) for t in ts]
+        dg().decompress_data(False, [comp[i, :hs[i]] for i in range(64)], outs, prob_bits=pb)
+        for i in range(64):
+            assert torch.equal(outs[i], ts[i])
+
+
+@pytest.mark.parametrize("kind,batch,relu", [("bf16", 64, False), ("f16", 256, True)])
+def test_config3_4_float_256mib_roundtrip(kind, batch, relu):
+    # BASELINE configs[2]/[3]: 256 MiB of 16-bit floats; round trip + oracle equality on one member
+    per = (128 << 20) // batch
+    uniq = [normal_words(per, kind, 1234 + i, relu=relu) for i in range(4)]
+    dev = [words_to_tensor(u, kind) for u in uniq]
+    ts = [dev[i % 4] for i in range(batch)]
+    comp, sizes, _ = dg().compress_data(True, ts)
+    hs = sizes.cpu().tolist()
+    want = O.float_compress(KINDS[kind][0], uniq[0], 10)
+    assert hs[0] == want.size and np.array_equal(comp[0, :hs[0]].cpu().numpy(), want)
+    outs = [torch.empty_like(t) for t in ts]
+    dg().decompress_data(True, [comp[i, :hs[i]] for i in range(batch)], outs)
+    for i in range(batch):
+        assert torch.equal(outs[i].view(torch.int16), ts[i].view(torch.int16))
+
+
+def test_single_member_256mib_bf16():
+    # bs = 1 x 128 Mi floats: 32768 blocks in one member (look-back across many tickets)
+    w = words_to_tensor(normal_words(128 << 20, "bf16", 99), "bf16")
+    comp, sizes, _ = dg().compress_data(True, [w])
+    n = int(sizes[0])
+    ratio = n / (w.numel() * 2)
+    assert 0.66 < ratio < 0.69  # README: ~0.673
+    out = torch.empty_like(w)
+    dg().decompress_data(True, [comp[0, :n]], [out])
+    assert torch.equal(out.view(torch.int16), w.view(torch.int16))
+
+
+def test_kernel_variants_agree():
+    # every tuning variant produces identical results
+    from dietgpu_b200 import capi
+
+    a = [zipf_bytes(300000, 1.1, 5), exp_bytes(4097, 50, 6)]
+    try:
+        for stage in (0, 1):
+            for dw in (2, 4, 8):
+                for ew in (2, 4, 8, 16):
+                    capi.set_option("decode_stage", stage)
+                    capi.set_option("decode_warps", dw)
+                    capi.set_option("encode_warps", ew)
+                    ans_roundtrip(a, 10)
+    finally:
+        capi.set_option("decode_stage", 1)
+        capi.set_option("decode_warps", 4)
+        capi.set_option("encode_warps", 8)
