@@ -1,0 +1,497 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode throughput of the batched rANS / float codec.
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--workload c3|c2|c4|c3x1]
+
+A "step" = one pass of the hot path over one batch: compress the whole batch,
+then decompress it.  metric = uncompressed GB/s through encode+decode
+= 2 * uncompressed_bytes / (t_encode + t_decode)   [the reference's convention
+is uncompressed bytes / time, benchmark.py:156-157].
+
+Workloads (BASELINE.json configs; MiB-based like the reference's benchmark.py):
+  c3    64 x 2 Mi bf16 N(0,1)            (256 MiB)  <- default / headline
+  c2    64 x 4 MiB Zipf(s=1) bytes, pb10 (256 MiB)
+  c4    256 x 512 Ki fp16 ReLU(N(0,1))   (256 MiB)
+  c3x1  1 x 128 Mi bf16 N(0,1)           (256 MiB, batch 1 -- the published A100 curve point)
+
+N > 1 (torchrun, one rank per GPU): every rank codes its own batch (seed offset
+1000*rank): weak scaling, no data-path collective (batch members are
+independent); NCCL is only used for the barrier / max-over-ranks timing and one
+all-gather of the compressed sizes.
+
+--impl reference runs the UNMODIFIED reference (oracle/_ref/libdietgpu_ref.so,
+built from /root/reference for sm_100a by oracle/build_ref.sh) through the same
+harness on the GPU.  DietGPU has no CPU implementation, so "the reference's own
+implementation of the path" is its CUDA code; the host-CPU number both arms
+report under `cpu_baseline` is the oracle port (oracle/dietgpu_oracle.c,
+OpenMP over all host cores).  If oracle/_ref is missing the reference arm falls
+back to timing that CPU port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MIB = 1 << 20
+WORKLOADS = {
+    # name: (kind, batch, elems per member, description)
+    "c3": ("bf16", 64, 2 * MIB, "64 x 2Mi bf16 N(0,1) = 256 MiB, prec 10 (BASELINE configs[2])"),
+    "c2": ("bytes", 64, 4 * MIB, "64 x 4MiB Zipf(s=1) bytes = 256 MiB, prec 10 (BASELINE configs[1])"),
+    "c4": ("f16", 256, 512 * 1024, "256 x 512Ki fp16 ReLU(N(0,1)) = 256 MiB, prec 10 (BASELINE configs[3])"),
+    "c3x1": ("bf16", 1, 128 * MIB, "1 x 128Mi bf16 N(0,1) = 256 MiB, batch 1, prec 10"),
+}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batch(torch, kind, batch, per, seed, device):
+    g = torch.Generator(device=device).manual_seed(seed)
+    ts = []
+    if kind == "bytes":
+        p = 1.0 / torch.arange(1, 257, dtype=torch.float64, device=device)
+        p = (p / p.sum()).float()
+        for _ in range(batch):
+            ts.append(torch.multinomial(p, per, replacement=True, generator=g).to(torch.uint8))
+    else:
+        dt = torch.bfloat16 if kind == "bf16" else torch.float16
+        for _ in range(batch):
+            x = torch.randn(per, generator=g, device=device, dtype=torch.float32)
+            if kind == "f16":
+                x = torch.relu(x)
+            ts.append(x.to(dt))
+    return ts
+
+
+class OursCodec:
+    name = "ours"
+
+    def __init__(self, torch, kind, ts):
+        import dietgpu_b200 as dg
+        self.dg, self.torch, self.kind, self.ts = dg, torch, kind, ts
+        self.as_float = kind != "bytes"
+        n = len(ts)
+        dev = ts[0].device
+        _, cols = (dg.max_float_compressed_output_size(ts) if self.as_float else dg.max_any_compressed_output_size(ts))
+        self.comp = torch.empty((n, cols), dtype=torch.uint8, device=dev)
+        self.sizes = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.outs = [torch.empty_like(t) for t in ts]
+        L = dg.capi.lib()
+        mx = max(t.numel() for t in ts)
+        if self.as_float:
+            ft = dg.ops._float_type(ts[0])
+            need = max(L.dgb_float_compress_temp_bytes(ft, n, mx), L.dgb_float_decompress_temp_bytes(ft, n, mx))
+        else:
+            need = max(L.dgb_ans_encode_temp_bytes(n, mx), L.dgb_ans_decode_temp_bytes(n))
+        self.temp = torch.empty(need + 512, dtype=torch.uint8, device=dev)
+        self.rows = None
+
+    def encode(self):
+        self.dg.compress_data(self.as_float, self.ts, False, self.temp, self.comp, self.sizes)
+
+    def bind_rows(self):
+        hs = self.sizes.cpu().tolist()
+        self.rows = [self.comp[i, :hs[i]] for i in range(len(self.ts))]
+        return hs
+
+    def decode(self):
+        self.dg.decompress_data(self.as_float, self.rows, self.outs, False, self.temp)
+
+    launches_per_step = 4  # stats + encode + plan + decode
+
+
+class RefGpuCodec:
+    name = "reference"
+
+    def __init__(self, torch, kind, ts):
+        from oracle import ref_lib
+        self.torch, self.kind, self.ts = torch, kind, ts
+        self.as_float = kind != "bytes"
+        self.ft = {"bf16": 2, "f16": 1}.get(kind, 0)
+        n = len(ts)
+        dev = ts[0].device
+        L = ref_lib.lib()
+        mx = max(t.numel() for t in ts)
+        cols = L.ref_float_max_compressed_size(self.ft, mx) if self.as_float else L.ref_ans_max_compressed_size(mx)
+        self.comp = torch.empty((n, cols), dtype=torch.uint8, device=dev)
+        self.sizes = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.outs = [torch.empty_like(t) for t in ts]
+        total = sum(t.numel() * t.element_size() for t in ts)
+        self.codec = ref_lib.RefCodec(int(2.0 * total) + 256 * MIB, dev)  # no cudaMalloc fallback
+        self.rows = None
+
+    def encode(self):
+        if self.as_float:
+            self.codec.float_compress(self.ft, self.ts, self.comp, self.sizes)
+        else:
+            self.codec.ans_encode(self.ts, self.comp, self.sizes)
+
+    def bind_rows(self):
+        hs = self.sizes.cpu().tolist()
+        self.rows = [self.comp[i, :hs[i]] for i in range(len(self.ts))]
+        return hs
+
+    def decode(self):
+        if self.as_float:
+            self.codec.float_decompress(self.ft, self.rows, self.outs)
+        else:
+            self.codec.ans_decode(self.rows, self.outs)
+
+    launches_per_step = 0
+
+
+def cpu_baseline(kind, batch, per, budget_s=12.0):
+    """Oracle port (OpenMP) on the host cores, bounded sample of the same workload."""
+    import numpy as np
+    import torch
+
+    from oracle import oracle as O
+
+    cores = O.num_threads()
+    g = torch.Generator().manual_seed(4321)
+    members = min(batch, 8)
+    arrs = []
+    for _ in range(members):
+        if kind == "bytes":
+            p = 1.0 / np.arange(1, 257)
+            p /= p.sum()
+            arrs.append(np.random.default_rng(4321).choice(256, size=per, p=p).astype(np.uint8))
+        else:
+            x = torch.randn(per, generator=g)
+            if kind == "f16":
+                arrs.append(torch.relu(x).to(torch.float16).view(torch.int16).numpy().view(np.uint16))
+            else:
+                arrs.append(x.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16))
+    ft = {"bf16": O.BF16, "f16": O.F16}.get(kind)
+    nbytes = sum(a.nbytes for a in arrs)
+    t_enc = t_dec = 0.0
+    reps = 0
+    t0 = time.perf_counter()
+    while reps < 1 or (time.perf_counter() - t0 < budget_s and reps < 20):
+        for a in arrs:
+            s = time.perf_counter()
+            arch = O.ans_encode(a, 10) if ft is None else O.float_compress(ft, a, 10)
+            m = time.perf_counter()
+            rc, out, _ = O.ans_decode(arch, 10) if ft is None else O.float_decompress(ft, arch, 10)
+            e = time.perf_counter()
+            assert rc == 0
+            t_enc += m - s
+            t_dec += e - m
+        reps += 1
+    total = nbytes * reps
+    return {
+        "value": round(2 * total / (t_enc + t_dec) / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+        "encode_gbs": round(total / t_enc / 1e9, 3), "decode_gbs": round(total / t_dec / 1e9, 3),
+        "sample": f"{members} members x {reps} reps of the workload ({nbytes / MIB:.0f} MiB per rep), "
+                  f"oracle/dietgpu_oracle.c with OpenMP over blocks",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--all-workloads", action="store_true", help="add encode/decode GB/s of every workload under 'detail'")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; dietgpu_b200 has no CPU fallback"}))
+        sys.exit(1)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from oracle import ref_lib
+    use_ref_gpu = args.impl == "reference" and ref_lib.available()
+    if args.impl == "reference" and not use_ref_gpu:
+        # no compiled reference here: the reference arm is the CPU port
+        if rank == 0:
+            kind, batch, per, desc = WORKLOADS[args.workload]
+            cb = cpu_baseline(kind, batch, per, budget_s=60.0)
+            line = {"metric": "encode+decode GB/s (uncompressed bytes / time)", "value": cb["value"], "unit": "GB/s",
+                    "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "u8/u32 integer", "data": "synthetic", "config": {"workload": desc},
+                    "cpu_baseline": cb,
+                    "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+        return
+
+    def run_workload(name, steps, warmup, full):
+        kind, batch, per, desc = WORKLOADS[name]
+        ts = make_batch(torch, kind, batch, per, 1234 + 1000 * rank, dev)
+        codec = RefGpuCodec(torch, kind, ts) if use_ref_gpu else OursCodec(torch, kind, ts)
+        ubytes = sum(t.numel() * t.element_size() for t in ts)
+        stream = torch.cuda.current_stream()
+
+        codec.encode()
+        hs = codec.bind_rows()
+        codec.decode()
+        torch.cuda.synchronize()
+        it = torch.int16 if kind != "bytes" else torch.uint8
+        verified = all(torch.equal(a.view(it), b.view(it)) for a, b in zip(ts, codec.outs))
+        cbytes = int(sum(hs))
+
+        for _ in range(warmup):
+            codec.encode()
+            codec.decode()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if full and rank == 0:
+            sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+        ev[0].record(stream)
+        for i in range(steps):
+            codec.encode()
+            ev[2 * i + 1].record(stream)
+            codec.decode()
+            ev[2 * i + 2].record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if (full and rank == 0) else None
+        t_enc = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)) / 1e3
+        t_dec = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)) / 1e3
+        t_tot = ev[0].elapsed_time(ev[2 * steps]) / 1e3
+        if world > 1:
+            tt = torch.tensor([t_tot, t_enc, t_dec], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_tot, t_enc, t_dec = tt.tolist()
+            # plumbing only: every rank learns every archive size
+            allsz = torch.empty(world * len(hs), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(allsz, codec.sizes)
+            cbytes_all = int(allsz.sum().item())
+        else:
+            cbytes_all = cbytes
+        res = {
+            "desc": desc, "kind": kind, "batch": batch, "ubytes": ubytes, "cbytes": cbytes,
+            "ratio": round(cbytes / ubytes, 4), "verified": bool(verified),
+            "t_tot": t_tot, "t_enc": t_enc, "t_dec": t_dec,
+            "encode_gbs": world * ubytes * steps / t_enc / 1e9, "decode_gbs": world * ubytes * steps / t_dec / 1e9,
+            "value": world * 2 * ubytes * steps / t_tot / 1e9, "clocks": clocks, "cbytes_all": cbytes_all,
+        }
+        if not full:
+            return res
+
+        # ---- per-kernel durations (CUDA events around every launch, same stream) ----
+        if not use_ref_gpu:
+            from dietgpu_b200 import capi
+            capi.set_option("timing", 1)
+            capi.kernel_times()
+            for _ in range(steps):
+                codec.encode()
+                codec.decode()
+            kt = capi.kernel_times()
+            capi.set_option("timing", 0)
+            res["kernels"] = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for k, v in kt.items() if v[1]}
+
+        # ---- end to end through the public API with HOST buffers ----
+        pin_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in ts]
+        pin_comp = torch.empty(codec.comp.shape, dtype=torch.uint8, pin_memory=True)
+        pin_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in ts]
+        e2e_steps = max(2, min(steps, 5))
+        h2d = d2h = 0
+
+        def e2e_step():
+            nonlocal h2d, d2h
+            for t, p in zip(ts, pin_in):          # host -> device: the step's inputs
+                t.copy_(p, non_blocking=True)
+            codec.encode()
+            hs2 = codec.sizes.cpu().tolist()      # device -> host: sizes, then the archives
+            for i, n in enumerate(hs2):
+                pin_comp[i, :n].copy_(codec.comp[i, :n], non_blocking=True)
+            torch.cuda.synchronize()
+            for i, n in enumerate(hs2):           # host -> device: the archives
+                codec.comp[i, :n].copy_(pin_comp[i, :n], non_blocking=True)
+            codec.rows = [codec.comp[i, :n] for i, n in enumerate(hs2)]
+            codec.decode()
+            for o, p in zip(codec.outs, pin_out):  # device -> host: the decoded floats
+                p.copy_(o, non_blocking=True)
+            torch.cuda.synchronize()
+            h2d = ubytes + sum(hs2)
+            d2h = sum(hs2) + 4 * len(hs2) + ubytes
+
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = tt.item()
+        e2e_ok = all(torch.equal(a.view(it), b.view(it).to(dev)) for a, b in zip(ts, pin_out))
+        res["e2e"] = {"value": round(world * 2 * ubytes * e2e_steps / t_e2e / 1e9, 3), "unit": "GB/s",
+                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                      "verified": bool(e2e_ok),
+                      "note": "pinned host input -> H2D -> compress -> D2H archives -> H2D archives -> decompress -> D2H output"}
+        return res
+
+    main_res = run_workload(args.workload, args.steps, args.warmup, True)
+    kind = main_res["kind"]
+    peak, peak_src = load_peaks()
+    ubytes, cbytes, steps = main_res["ubytes"], main_res["cbytes"], args.steps
+
+    # ---- roofline (algorithmic bytes per launch / event-timed duration of that kernel) ----
+    roofline = None
+    roofline_all = {}
+    if "kernels" in main_res:
+        # compulsory bytes per launch given the two-kernel split of each direction:
+        #   floats: stats  reads 2F(words) writes the stored plane(s) + header, decode reads C_f writes 2F
+        #   encode reads the F comp bytes and writes the ANS archive
+        nfl = ubytes // (2 if kind in ("bf16", "f16") else 1)
+        if kind == "bytes":
+            alg = {"stats": ubytes, "encode": ubytes + cbytes, "decode": cbytes + ubytes}
+        else:
+            ans_bytes = cbytes - (nfl + 16 * main_res["batch"])
+            alg = {"stats": ubytes + nfl, "encode": nfl + ans_bytes, "decode": cbytes + ubytes}
+        for k, v in main_res["kernels"].items():
+            if k in alg:
+                a = alg[k] / (v["ms_avg"] / 1e3) / 1e9
+                roofline_all[k] = {"bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
+                                   "frac": round(a / peak, 4), "ms": round(v["ms_avg"], 4),
+                                   "algorithmic_bytes": int(alg[k])}
+        dom = max(roofline_all, key=lambda k: roofline_all[k]["ms"])
+        roofline = dict(roofline_all[dom])
+        roofline.update({"kernel": dom, "traffic": None, "peak_source": peak_src})
+        # direction-level figures (encode = decode = 2F + C_f algorithmic bytes)
+        for d, t in (("encode_direction", main_res["t_enc"]), ("decode_direction", main_res["t_dec"])):
+            a = (ubytes + cbytes) * steps / t / 1e9
+            roofline_all[d] = {"achieved": round(a, 1), "frac": round(a / peak, 4), "unit": "GB/s"}
+
+    detail = {}
+    if args.all_workloads:
+        for w in sorted(WORKLOADS):
+            r = main_res if w == args.workload else run_workload(w, max(3, args.steps // 4), 3, False)
+            detail[w] = {"encode_gbs": round(r["encode_gbs"], 1), "decode_gbs": round(r["decode_gbs"], 1),
+                         "ratio": r["ratio"], "verified": r["verified"]}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        kind_, batch_, per_, _ = WORKLOADS[args.workload]
+        cb = cpu_baseline(kind_, batch_, per_)
+
+    if rank == 0:
+        codec_launches = OursCodec.launches_per_step if not use_ref_gpu else 0
+        line = {
+            "metric": "encode+decode GB/s (uncompressed bytes / time)",
+            "value": round(main_res["value"], 2), "unit": "GB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(main_res["t_tot"] / args.steps * 1e3, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 integer state machine on u8 symbols", "data": "synthetic",
+            "config": {"workload": main_res["desc"], "batch": main_res["batch"],
+                       "uncompressed_bytes_per_gpu": ubytes, "compressed_bytes_per_gpu": cbytes,
+                       "ratio": main_res["ratio"], "prob_bits": 10, "checksum": False,
+                       "l2": "inputs (256 MiB) + archives (~172 MiB) exceed the 126 MB L2; no explicit flush",
+                       "parallelism": f"batch shard x{world}, no data-path collective"},
+            "encode_gbs": round(main_res["encode_gbs"], 2), "decode_gbs": round(main_res["decode_gbs"], 2),
+            "verified_roundtrip": main_res["verified"],
+            "gpu_launches": codec_launches * args.steps,
+            "clocks": main_res["clocks"],
+            "e2e": main_res.get("e2e"),
+        }
+        if use_ref_gpu:
+            line["impl"] = "reference"
+            line["reference_kind"] = "reference CUDA path (oracle/_ref/libdietgpu_ref.so, sm_100a build of /root/reference)"
+        if roofline:
+            line["roofline"] = roofline
+            line["roofline_all"] = roofline_all
+        if cb:
+            line["cpu_baseline"] = cb
+        if detail:
+            line["detail"] = detail
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,7 +26,7 @@ SYMBOLS = [
     "dgb_float_compress_pointer", "dgb_float_compress_split_size",
     "dgb_float_decompress_pointer", "dgb_float_decompress_split_size",
     "dgb_float_get_compressed_info",
-    "dgb_set_option", "dgb_get_option",
+    "dgb_set_option", "dgb_get_option", "dgb_kernel_times",
 ]
 
 
@@ -94,6 +94,8 @@ def lib():
     L.dgb_set_option.argtypes = [C.c_char_p, i32]
     L.dgb_get_option.restype = i32
     L.dgb_get_option.argtypes = [C.c_char_p, C.POINTER(i32)]
+    L.dgb_kernel_times.restype = i32
+    L.dgb_kernel_times.argtypes = [vp, vp, i32]
     _lib = L
     return L
 
@@ -123,3 +125,14 @@ def ptr_array(ptrs):
 
 def u32_array(vals):
     return (C.c_uint32 * len(vals))(*[int(v) for v in vals])
+
+
+KERNEL_SLOTS = ["stats", "encode", "plan", "decode", "checksum"]
+
+
+def kernel_times():
+    """(ms, launches) per kernel slot since the last call (option "timing" must be 1)."""
+    ms = (C.c_float * len(KERNEL_SLOTS))()
+    cnt = (C.c_int * len(KERNEL_SLOTS))()
+    check(lib().dgb_kernel_times(ms, cnt, len(KERNEL_SLOTS)), "kernel_times")
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(KERNEL_SLOTS)}

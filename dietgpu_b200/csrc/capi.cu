@@ -18,6 +18,33 @@ Options& options() {
 static thread_local cudaError_t tlsLastCuda = cudaSuccess;
 void setLastCudaError(cudaError_t e) { tlsLastCuda = e; }
 
+// ---- per-kernel timing -------------------------------------------------------
+namespace {
+struct TimedLaunch { int slot; cudaEvent_t a, b; };
+std::vector<TimedLaunch>& timedLaunches() { static std::vector<TimedLaunch> v; return v; }
+std::vector<cudaEvent_t>& eventPool() { static std::vector<cudaEvent_t> v; return v; }
+cudaEvent_t takeEvent() {
+  auto& pool = eventPool();
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+thread_local TimedLaunch tlsOpen[kNumSlots];
+}  // namespace
+
+void timerBegin(int slot, cudaStream_t stream) {
+  if (!options().timing) return;
+  TimedLaunch t{slot, takeEvent(), takeEvent()};
+  cudaEventRecord(t.a, stream);
+  tlsOpen[slot] = t;
+}
+void timerEnd(int slot, cudaStream_t stream) {
+  if (!options().timing) return;
+  cudaEventRecord(tlsOpen[slot].b, stream);
+  timedLaunches().push_back(tlsOpen[slot]);
+}
+
 namespace {
 
 bool validFloatType(int ft) { return ft == DGB_FLOAT16 || ft == DGB_BFLOAT16 || ft == DGB_FLOAT32; }
@@ -248,9 +275,12 @@ static int* optionSlot(const char* name) {
   if (!name) return nullptr;
   if (!std::strcmp(name, "decode_stage")) return &o.decode_stage;
   if (!std::strcmp(name, "decode_warps")) return &o.decode_warps;
+  if (!std::strcmp(name, "decode_lut64")) return &o.decode_lut64;
+  if (!std::strcmp(name, "decode_slot_words")) return &o.decode_slot_words;
   if (!std::strcmp(name, "encode_warps")) return &o.encode_warps;
   if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
   if (!std::strcmp(name, "hist_mode")) return &o.hist_mode;
+  if (!std::strcmp(name, "timing")) return &o.timing;
   return nullptr;
 }
 
@@ -258,6 +288,22 @@ int dgb_set_option(const char* name, int value) {
   int* s = optionSlot(name);
   if (!s) return DGB_ERR_INVALID_ARG;
   *s = value;
+  return DGB_OK;
+}
+
+// Sum of the event-timed durations (ms) and launch counts per kernel slot since the last
+// call; synchronises the device.  Slots: 0 stats(K1) 1 encode(K2) 2 plan 3 decode 4 checksum.
+int dgb_kernel_times(float* ms, int* counts, int nslots) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return DGB_ERR_CUDA;
+  for (int i = 0; i < nslots; ++i) { if (ms) ms[i] = 0.f; if (counts) counts[i] = 0; }
+  for (auto& t : timedLaunches()) {
+    float e = 0.f;
+    cudaEventElapsedTime(&e, t.a, t.b);
+    if (t.slot < nslots) { if (ms) ms[t.slot] += e; if (counts) counts[t.slot] += 1; }
+    eventPool().push_back(t.a);
+    eventPool().push_back(t.b);
+  }
+  timedLaunches().clear();
   return DGB_OK;
 }
 

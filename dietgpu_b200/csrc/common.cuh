@@ -65,10 +65,13 @@ struct __align__(16) EncEntry {
 // ---- tuning options (dgb_set_option) ---------------------------------------
 struct Options {
   int decode_stage = 1;      // 1: stream staged into smem with cp.async.bulk (TMA); 0: direct LDG
-  int decode_warps = 4;      // warps per decode CTA
+  int decode_warps = 4;      // warps per decode CTA (4 or 8)
+  int decode_lut64 = 0;      // 1: 8-byte decode LUT entries (fewer ALU ops, more smem)
+  int decode_slot_words = 0; // TMA staging slot per warp in u16 words; 0 = auto
   int encode_warps = 8;      // warps per encode CTA (one 4 KiB block each per ticket)
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_mode = 0;         // 0: per-warp smem atomics; 1: per-lane private byte counters
+  int timing = 0;            // 1: bracket every kernel launch with CUDA events (bench.py roofline pass)
 };
 Options& options();
 
@@ -92,6 +95,12 @@ int getInfo(int kind, void* temp, size_t tempBytes, const void* const* in, bool 
             cudaStream_t stream);
 
 void setLastCudaError(cudaError_t e);
+
+// Per-kernel timing (options().timing): slots are stable indices reported by
+// dgb_kernel_times().  No-ops when timing is off.
+enum TimerSlot : int { kSlotStats = 0, kSlotEncode = 1, kSlotPlan = 2, kSlotDecode = 3, kSlotChecksum = 4, kNumSlots = 5 };
+void timerBegin(int slot, cudaStream_t stream);
+void timerEnd(int slot, cudaStream_t stream);
 
 #define DGB_CUDA_TRY(expr)                    \
   do {                                        \

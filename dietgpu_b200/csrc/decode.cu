@@ -25,6 +25,14 @@
 
 #include "common.cuh"
 
+// rows per software-pipelined group and the resident-warp target that caps registers
+#ifndef DGB_DECODE_UNROLL
+#define DGB_DECODE_UNROLL 8
+#endif
+#ifndef DGB_DECODE_WARPS_PER_SM
+#define DGB_DECODE_WARPS_PER_SM 48
+#endif
+
 namespace dgb {
 
 namespace {
@@ -113,60 +121,103 @@ planKernel(DecodeScratch sc, uint32_t n, int pb, uint8_t* __restrict__ outSucces
 // ---------------------------------------------------------------------------
 // Output writers (ans/BatchProvider.cuh:16-37 BatchWriter, float/
 // GpuFloatDecompress.cuh:391-486 JoinFloatWriter restated).  A writer is bound
-// to one 4 KiB block; `at(row)` yields a cursor for a group of rows so that the
-// unrolled loop addresses rows with compile-time offsets (row J of the group is
-// element J*32 from the cursor).  `prefetch` fetches the stored byte(s) of a
-// row ahead of the dependent decode chain.
+// to one 4 KiB block.  The float kinds need the stored ("non-compressed")
+// byte(s) of every element: those are streamed into a small per-warp
+// shared-memory ring with cp.async (LDGSTS) -- one 16 B copy per lane covers a
+// whole group of 8 rows -- two groups ahead of the row being decoded, so the
+// join reads them with an LDS and the HBM latency of the stored plane never
+// meets the dependent decode chain (ncu, first version: 46 % of all stall
+// samples were long-scoreboard waits on per-row LDG.U8 of these bytes; holding
+// them in registers instead made ptxas sink the loads next to their use).
 // ---------------------------------------------------------------------------
+constexpr int kGroupRows = 8;       // rows per prefetch group
+constexpr uint32_t kRingSlots = 4;  // groups resident per warp (current + 2 in flight + 1 spare)
+
+__device__ __forceinline__ void cpAsync16(uint32_t dstSmem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstSmem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpAsyncWait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t ldsU16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+
 template <int KIND>
 struct RowWriter;
 
 template <>
 struct RowWriter<kKindBytes> {
+  static constexpr uint32_t kRingSlotBytes = 0;
   uint8_t* out;
-  struct Pre {};
   struct Cursor { uint8_t* o; };
+  __device__ __forceinline__ void setRing(uint32_t, uint32_t) {}
   __device__ __forceinline__ void setBlock(const ArchiveView&, void* outBase, uint32_t block, uint32_t lane) {
     out = static_cast<uint8_t*>(outBase) + (size_t)block * kBlockBytes + lane;
     __builtin_assume(__isGlobal(out));
   }
-  __device__ __forceinline__ Cursor at(uint32_t row) const { return Cursor{out + row * 32u}; }
+  __device__ __forceinline__ Cursor at(uint32_t row, uint32_t) const { return Cursor{out + row * 32u}; }
+  __device__ __forceinline__ void issue(uint32_t, uint32_t) const {}
   template <int J>
-  __device__ __forceinline__ Pre prefetch(const Cursor&) const { return Pre{}; }
-  template <int J>
-  __device__ __forceinline__ void write(const Cursor& c, uint32_t entry, Pre) const {
+  __device__ __forceinline__ void write(const Cursor& c, uint32_t entry) const {
     c.o[J * 32] = (uint8_t)entry;
   }
+  // rows outside the pipelined groups
+  __device__ __forceinline__ void writeSlow(uint32_t row, uint32_t entry) const { out[row * 32u] = (uint8_t)entry; }
 };
 
 template <int KIND>
 struct RowWriter16 {
+  static constexpr uint32_t kRingSlotBytes = kGroupRows * 32;  // one stored byte per element
   uint16_t* out;
-  const uint8_t* non;
-  typedef uint32_t Pre;
-  struct Cursor { uint16_t* o; const uint8_t* n; };
-  __device__ __forceinline__ void setBlock(const ArchiveView& av, void* outBase, uint32_t block, uint32_t lane) {
-    out = static_cast<uint16_t*>(outBase) + (size_t)block * kBlockBytes + lane;
-    non = av.non + (size_t)block * kBlockBytes + lane;
+  const uint8_t* non;      // this lane's byte of row 0 of the block
+  const uint8_t* nonCopy;  // copy source of this lane (lanes 0..15 move 16 B each per group)
+  uint32_t ring, lane;
+  struct Cursor { uint16_t* o; uint32_t s; };
+  __device__ __forceinline__ void setRing(uint32_t ringAddr, uint32_t l) { ring = ringAddr; lane = l; }
+  __device__ __forceinline__ void setBlock(const ArchiveView& av, void* outBase, uint32_t block, uint32_t l) {
+    out = static_cast<uint16_t*>(outBase) + (size_t)block * kBlockBytes + l;
+    non = av.non + (size_t)block * kBlockBytes + l;
+    nonCopy = av.non + (size_t)block * kBlockBytes + l * 16u;
     __builtin_assume(__isGlobal(out));
     __builtin_assume(__isGlobal(non));
+    __builtin_assume(__isGlobal(nonCopy));
   }
-  __device__ __forceinline__ Cursor at(uint32_t row) const { return Cursor{out + row * 32u, non + row * 32u}; }
-  template <int J>
-  __device__ __forceinline__ Pre prefetch(const Cursor& c) const { return __ldg(c.n + J * 32); }
-  template <int J>
-  __device__ __forceinline__ void write(const Cursor& c, uint32_t entry, Pre nc) const {
-    uint32_t v;
+  // cursor of the group starting at `row`, resident in ring slot `slot`
+  __device__ __forceinline__ Cursor at(uint32_t row, uint32_t slot) const {
+    return Cursor{out + row * 32u, ring + slot * kRingSlotBytes + lane};
+  }
+  // request rows [row, row + 8) into ring slot `slot`
+  __device__ __forceinline__ void issue(uint32_t row, uint32_t slot) const {
+    if (lane < 16u) cpAsync16(ring + slot * kRingSlotBytes + lane * 16u, nonCopy + row * 32u);
+  }
+  static __device__ __forceinline__ uint32_t join(uint32_t entry, uint32_t nc) {
     if (KIND == kKindF16) {
       // float/GpuFloatUtils.cuh:117-119: comp * 256 + nonComp  (bytes: [non, comp])
-      v = __byte_perm(entry, nc, 0x4404);
-    } else {
-      // float/GpuFloatUtils.cuh:149-159: (comp:non) rotated right by one within 16 bits.
-      // x = comp<<24 | non<<16 ; (non : x) >> 17 leaves comp<<7 | non>>1 | (non&1)<<15 in the
-      // low 16 bits (higher bits are dropped by the 16-bit store)
-      v = __funnelshift_r(__byte_perm(entry, nc, 0x0444), nc, 17);
+      return __byte_perm(entry, nc, 0x4404);
     }
-    c.o[J * 32] = (uint16_t)v;
+    // float/GpuFloatUtils.cuh:149-159: (comp:non) rotated right by one within 16 bits.
+    // x = comp<<24 | non<<16 ; (non : x) >> 17 leaves comp<<7 | non>>1 | (non&1)<<15 in the
+    // low 16 bits (higher bits are dropped by the 16-bit store)
+    return __funnelshift_r(__byte_perm(entry, nc, 0x0444), nc, 17);
+  }
+  template <int J>
+  __device__ __forceinline__ void write(const Cursor& c, uint32_t entry) const {
+    c.o[J * 32] = (uint16_t)join(entry, ldsU8<J * 32>(c.s));
+  }
+  __device__ __forceinline__ void writeSlow(uint32_t row, uint32_t entry) const {
+    out[row * 32u] = (uint16_t)join(entry, __ldg(non + row * 32u));
   }
 };
 template <> struct RowWriter<kKindF16> : RowWriter16<kKindF16> {};
@@ -174,144 +225,226 @@ template <> struct RowWriter<kKindBF16> : RowWriter16<kKindBF16> {};
 
 template <>
 struct RowWriter<kKindF32> {
+  // per group: 8 rows x 64 B of the u16 plane, then 8 rows x 32 B of the u8 plane
+  static constexpr uint32_t kRingSlotBytes = kGroupRows * 96;
   uint32_t* out;
   const uint16_t* non2;
   const uint8_t* non1;
-  struct Pre { uint32_t lo, hi; };
-  struct Cursor { uint32_t* o; const uint16_t* n2; const uint8_t* n1; };
-  __device__ __forceinline__ void setBlock(const ArchiveView& av, void* outBase, uint32_t block, uint32_t lane) {
-    out = static_cast<uint32_t*>(outBase) + (size_t)block * kBlockBytes + lane;
-    non2 = reinterpret_cast<const uint16_t*>(av.non) + (size_t)block * kBlockBytes + lane;
-    non1 = av.non + 2u * (size_t)roundUp(av.floatWords, 8u) + (size_t)block * kBlockBytes + lane;
+  const uint8_t* copy2;
+  const uint8_t* copy1;
+  uint32_t ring, lane;
+  struct Cursor { uint32_t* o; uint32_t s2, s1; };
+  __device__ __forceinline__ void setRing(uint32_t ringAddr, uint32_t l) { ring = ringAddr; lane = l; }
+  __device__ __forceinline__ void setBlock(const ArchiveView& av, void* outBase, uint32_t block, uint32_t l) {
+    out = static_cast<uint32_t*>(outBase) + (size_t)block * kBlockBytes + l;
+    const uint8_t* p2 = av.non + 2u * (size_t)block * kBlockBytes;
+    const uint8_t* p1 = av.non + 2u * (size_t)roundUp(av.floatWords, 8u) + (size_t)block * kBlockBytes;
+    non2 = reinterpret_cast<const uint16_t*>(p2) + l;
+    non1 = p1 + l;
+    copy2 = p2 + l * 16u;
+    copy1 = p1 + l * 16u;
     __builtin_assume(__isGlobal(out));
     __builtin_assume(__isGlobal(non2));
     __builtin_assume(__isGlobal(non1));
+    __builtin_assume(__isGlobal(copy2));
+    __builtin_assume(__isGlobal(copy1));
   }
-  __device__ __forceinline__ Cursor at(uint32_t row) const {
-    return Cursor{out + row * 32u, non2 + row * 32u, non1 + row * 32u};
+  __device__ __forceinline__ Cursor at(uint32_t row, uint32_t slot) const {
+    const uint32_t base = ring + slot * kRingSlotBytes;
+    return Cursor{out + row * 32u, base + lane * 2u, base + kGroupRows * 64 + lane};
+  }
+  __device__ __forceinline__ void issue(uint32_t row, uint32_t slot) const {
+    const uint32_t base = ring + slot * kRingSlotBytes;
+    cpAsync16(base + lane * 16u, copy2 + row * 64u);  // 32 lanes x 16 B = 8 rows x 64 B
+    if (lane < 16u) cpAsync16(base + kGroupRows * 64 + lane * 16u, copy1 + row * 32u);
+  }
+  static __device__ __forceinline__ uint32_t join(uint32_t entry, uint32_t lo, uint32_t hi) {
+    // float/GpuFloatUtils.cuh:187-190: (comp << 24 | stored 24 bits) rotated right by one
+    const uint32_t v = __byte_perm(lo, __byte_perm(hi, entry, 0x0040), 0x5410);
+    return __funnelshift_r(v, v, 1);
   }
   template <int J>
-  __device__ __forceinline__ Pre prefetch(const Cursor& c) const {
-    Pre p;
-    p.lo = __ldg(c.n2 + J * 32);
-    p.hi = __ldg(c.n1 + J * 32);
-    return p;
+  __device__ __forceinline__ void write(const Cursor& c, uint32_t entry) const {
+    c.o[J * 32] = join(entry, ldsU16<J * 64>(c.s2), ldsU8<J * 32>(c.s1));
   }
-  template <int J>
-  __device__ __forceinline__ void write(const Cursor& c, uint32_t entry, Pre p) const {
-    // float/GpuFloatUtils.cuh:187-190: rotate right by one
-    const uint32_t v = __byte_perm(p.lo, __byte_perm(p.hi, entry, 0x0040), 0x5410);
-    c.o[J * 32] = __funnelshift_r(v, v, 1);
+  __device__ __forceinline__ void writeSlow(uint32_t row, uint32_t entry) const {
+    out[row * 32u] = join(entry, __ldg(non2 + row * 32u), __ldg(non1 + row * 32u));
   }
 };
 
 // ---------------------------------------------------------------------------
-// One decode step for a full row (ans/GpuANSDecode.cuh:55-105 restated).
-// LUT entry: [31:20] pdf, [19:8] s-cdf, [7:0] symbol  (this kernel's own
-// layout; the LUT never leaves shared memory).
-// `words` points one past the last unread word of the block's stream, either
-// in shared memory (staged) or in global memory.
+// The compressed word stream of one block, read backwards.  Two flavours so the
+// hot loop always knows the address space: staged in shared memory by the TMA
+// bulk copy (LDS on the loop-carried path) or straight from global memory.
 // ---------------------------------------------------------------------------
+struct SmemStream {
+  uint32_t addr;  // shared BYTE address one past the last unread word
+  __device__ __forceinline__ uint32_t pop(uint32_t back) const {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr - 2u * back));
+    return v;
+  }
+  __device__ __forceinline__ void retreat(uint32_t cnt) { addr -= 2u * cnt; }
+};
+struct GmemStream {
+  const uint16_t* p;  // one past the last unread word
+  __device__ __forceinline__ uint32_t pop(uint32_t back) const { return __ldg(p - back); }
+  __device__ __forceinline__ void retreat(uint32_t cnt) { p -= cnt; }
+};
+
+// ---------------------------------------------------------------------------
+// Decode LUT, one entry per state residue (never leaves shared memory):
+//   LUT64 = false: u32  [31:20] pdf  [19:8] s-cdf  [7:0] symbol
+//   LUT64 = true : uint2 {pdf, (s-cdf) << 8 | symbol}   -- two fewer ALU ops per
+//                  row for the unpack, twice the shared-memory footprint
+// One decode step for a full row (ans/GpuANSDecode.cuh:55-105 restated); the
+// returned word has the decoded symbol in its low byte.
+// ---------------------------------------------------------------------------
+template <int PB, bool LUT64>
+struct Lut;
 template <int PB>
-__device__ __forceinline__ uint32_t decodeStep(uint32_t& state, const uint32_t* __restrict__ lut,
-                                               const uint16_t*& words, uint32_t geMask) {
-  constexpr uint32_t mask = (1u << PB) - 1u;
-  const uint32_t e = lut[state & mask];
-  state = (e >> 20) * (state >> PB) + ((e >> 8) & 0xfffu);
+struct Lut<PB, false> {
+  typedef uint32_t Entry;
+  static __device__ __forceinline__ Entry make(uint32_t pdf, uint32_t c, uint32_t sym) {
+    return (pdf << 20) | (c << 8) | sym;
+  }
+  static __device__ __forceinline__ uint32_t step(uint32_t& state, const Entry* __restrict__ lut) {
+    const uint32_t e = lut[state & ((1u << PB) - 1u)];
+    state = (e >> 20) * (state >> PB) + ((e >> 8) & 0xfffu);
+    return e;
+  }
+};
+template <int PB>
+struct Lut<PB, true> {
+  typedef uint2 Entry;
+  static __device__ __forceinline__ Entry make(uint32_t pdf, uint32_t c, uint32_t sym) {
+    return make_uint2(pdf, (c << 8) | sym);
+  }
+  static __device__ __forceinline__ uint32_t step(uint32_t& state, const Entry* __restrict__ lut) {
+    const uint2 e = lut[state & ((1u << PB) - 1u)];
+    state = e.x * (state >> PB) + (e.y >> 8);
+    return e.y;
+  }
+};
+
+// refill (ans/GpuANSDecode.cuh:89-101 restated): lanes whose state dropped below 2^15 pop one
+// word each, highest lane first
+template <typename Stream>
+__device__ __forceinline__ void refill(uint32_t& state, Stream& st, uint32_t geMask) {
   const bool rd = state < kStateMin;
   const uint32_t vote = __ballot_sync(0xffffffffu, rd);
-  if (rd) {
-    const uint32_t w = *(words - __popc(vote & geMask));
-    state = (state << 16) + w;
-  }
-  words -= __popc(vote);
+  if (rd) state = (state << 16) + st.pop(__popc(vote & geMask));
+  st.retreat(__popc(vote));
+}
+// shared-memory flavour in PTX: one predicate feeds the vote, the load and the state update
+template <>
+__device__ __forceinline__ void refill<SmemStream>(uint32_t& state, SmemStream& st, uint32_t geMask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 v, t, a, w;\n"
+      "setp.lt.u32 p, %0, 32768;\n"
+      "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+      "and.b32 t, v, %2;\n"
+      "popc.b32 t, t;\n"
+      "shl.b32 t, t, 1;\n"
+      "sub.u32 a, %1, t;\n"
+      "@p ld.shared.u16 w, [a];\n"
+      "@p mad.lo.u32 %0, %0, 65536, w;\n"
+      "popc.b32 t, v;\n"
+      "shl.b32 t, t, 1;\n"
+      "sub.u32 %1, %1, t;\n"
+      "}\n"
+      : "+r"(state), "+r"(st.addr)
+      : "r"(geMask));
+}
+
+template <int PB, bool LUT64, typename Stream>
+__device__ __forceinline__ uint32_t decodeStep(uint32_t& state,
+                                               const typename Lut<PB, LUT64>::Entry* __restrict__ lut,
+                                               Stream& st, uint32_t geMask) {
+  const uint32_t e = Lut<PB, LUT64>::step(state, lut);
+  refill(state, st, geMask);
   return e;
 }
 
-template <int PB>
+template <int PB, bool LUT64, typename Stream>
 __device__ __forceinline__ uint32_t decodeStepPartial(bool valid, uint32_t& state,
-                                                      const uint32_t* __restrict__ lut,
-                                                      const uint16_t*& words, uint32_t geMask) {
-  constexpr uint32_t mask = (1u << PB) - 1u;
-  const uint32_t e = lut[state & mask];
-  if (valid) state = (e >> 20) * (state >> PB) + ((e >> 8) & 0xfffu);
+                                                      const typename Lut<PB, LUT64>::Entry* __restrict__ lut,
+                                                      Stream& st, uint32_t geMask) {
+  uint32_t s2 = state;
+  const uint32_t e = Lut<PB, LUT64>::step(s2, lut);
+  if (valid) state = s2;
   const bool rd = valid && state < kStateMin;
   const uint32_t vote = __ballot_sync(0xffffffffu, rd);
-  if (rd) {
-    const uint32_t w = *(words - __popc(vote & geMask));
-    state = (state << 16) + w;
-  }
-  words -= __popc(vote);
+  if (rd) state = (state << 16) + st.pop(__popc(vote & geMask));
+  st.retreat(__popc(vote));
   return e;
 }
 
-template <int KIND, int PB, int J>
+template <int KIND, int PB, bool LUT64, typename Stream, int J>
 struct RowGroup {
+  typedef RowWriter<KIND> W;
   // rows J-1 .. 0 of the group, highest first (the decoder walks rows backwards)
-  template <typename PreArr>
-  static __device__ __forceinline__ void load(const RowWriter<KIND>& wr,
-                                              const typename RowWriter<KIND>::Cursor& c, PreArr& pre) {
-    pre[J - 1] = wr.template prefetch<J - 1>(c);
-    RowGroup<KIND, PB, J - 1>::load(wr, c, pre);
-  }
-  template <typename PreArr>
-  static __device__ __forceinline__ void run(uint32_t& state, const uint32_t* __restrict__ lut,
-                                             const uint16_t*& words, uint32_t geMask,
-                                             const RowWriter<KIND>& wr,
-                                             const typename RowWriter<KIND>::Cursor& c, PreArr& pre) {
-    const uint32_t e = decodeStep<PB>(state, lut, words, geMask);
-    wr.template write<J - 1>(c, e, pre[J - 1]);
-    RowGroup<KIND, PB, J - 1>::run(state, lut, words, geMask, wr, c, pre);
+  static __device__ __forceinline__ void run(uint32_t& state,
+                                             const typename Lut<PB, LUT64>::Entry* __restrict__ lut,
+                                             Stream& st, uint32_t geMask, const W& wr,
+                                             const typename W::Cursor& c) {
+    const uint32_t e = decodeStep<PB, LUT64>(state, lut, st, geMask);
+    wr.template write<J - 1>(c, e);
+    RowGroup<KIND, PB, LUT64, Stream, J - 1>::run(state, lut, st, geMask, wr, c);
   }
 };
-template <int KIND, int PB>
-struct RowGroup<KIND, PB, 0> {
-  template <typename PreArr>
-  static __device__ __forceinline__ void load(const RowWriter<KIND>&, const typename RowWriter<KIND>::Cursor&, PreArr&) {}
-  template <typename PreArr>
-  static __device__ __forceinline__ void run(uint32_t&, const uint32_t* __restrict__, const uint16_t*&, uint32_t,
-                                             const RowWriter<KIND>&, const typename RowWriter<KIND>::Cursor&, PreArr&) {}
+template <int KIND, int PB, bool LUT64, typename Stream>
+struct RowGroup<KIND, PB, LUT64, Stream, 0> {
+  typedef RowWriter<KIND> W;
+  static __device__ __forceinline__ void run(uint32_t&, const typename Lut<PB, LUT64>::Entry* __restrict__, Stream&,
+                                             uint32_t, const W&, const typename W::Cursor&) {}
 };
 
-template <int KIND, int PB>
-__device__ __forceinline__ void decodeBlockWarp(uint32_t state, const uint16_t* wordsEnd,
-                                                uint32_t n, const uint32_t* __restrict__ lut,
+template <int KIND, int PB, bool LUT64, typename Stream>
+__device__ __forceinline__ void decodeBlockWarp(uint32_t state, Stream st, uint32_t n,
+                                                const typename Lut<PB, LUT64>::Entry* __restrict__ lut,
                                                 const RowWriter<KIND>& wr, uint32_t lane) {
-  typedef typename RowWriter<KIND>::Pre Pre;
+  typedef typename RowWriter<KIND>::Cursor Cursor;
+  constexpr int U = kGroupRows;
+  typedef RowGroup<KIND, PB, LUT64, Stream, U> G;
   const uint32_t geMask = laneMaskGe();
-  const uint16_t* words = wordsEnd;
   uint32_t row = n >> 5;  // number of full rows; the partial row (if any) has this index
   const uint32_t rem = n & 31u;
+  // groups of U full rows are walked from the top: group k covers rows [row0 - U*(k+1), row0 - U*k)
+  const uint32_t row0 = row;
+  const uint32_t groups = row0 / U;
+  // stored bytes of the first two groups are requested before anything else
+  if (groups > 0) wr.issue(row0 - U, 0);
+  cpAsyncCommit();
+  if (groups > 1) wr.issue(row0 - 2 * U, 1);
+  cpAsyncCommit();
   if (rem) {
     const bool valid = lane < rem;
-    const typename RowWriter<KIND>::Cursor c = wr.at(row);
-    Pre pre[1] = {};
-    if (valid) pre[0] = wr.template prefetch<0>(c);
-    const uint32_t e = decodeStepPartial<PB>(valid, state, lut, words, geMask);
-    if (valid) wr.template write<0>(c, e, pre[0]);
+    const uint32_t e = decodeStepPartial<PB, LUT64>(valid, state, lut, st, geMask);
+    if (valid) wr.writeSlow(row, e);
   }
-  constexpr int U = 8;
-  while (row >= (uint32_t)U) {
+  for (uint32_t k = 0; k < groups; ++k) {
     row -= U;
-    const typename RowWriter<KIND>::Cursor c = wr.at(row);
-    Pre pre[U];
-    RowGroup<KIND, PB, U>::load(wr, c, pre);
-    RowGroup<KIND, PB, U>::run(state, lut, words, geMask, wr, c, pre);
+    if (k + 2 < groups) wr.issue(row - 2 * U, (k + 2) & (kRingSlots - 1));
+    cpAsyncCommit();
+    cpAsyncWait<2>();  // group k has landed (the two youngest may still be in flight)
+    __syncwarp();
+    const Cursor c = wr.at(row, k & (kRingSlots - 1));
+    G::run(state, lut, st, geMask, wr, c);
   }
   while (row > 0) {
     --row;
-    const typename RowWriter<KIND>::Cursor c = wr.at(row);
-    Pre pre[1];
-    pre[0] = wr.template prefetch<0>(c);
-    const uint32_t e = decodeStep<PB>(state, lut, words, geMask);
-    wr.template write<0>(c, e, pre[0]);
+    const uint32_t e = decodeStep<PB, LUT64>(state, lut, st, geMask);
+    wr.writeSlow(row, e);
   }
 }
 
 // LUT build from the archive's u16 pdf[256] (ans/GpuANSDecode.cuh:405-476
 // restated; runs inside the decode CTA).  blockDim.x == WARPS*32.
-template <int PB, int WARPS>
-__device__ void buildLut(const uint8_t* __restrict__ ans, uint32_t* __restrict__ lut,
+template <int PB, bool LUT64, int WARPS>
+__device__ void buildLut(const uint8_t* __restrict__ ans, typename Lut<PB, LUT64>::Entry* __restrict__ lut,
                          uint32_t* sPdf, uint32_t* sCdf, uint32_t* sWarp) {
   constexpr int T = WARPS * 32;
   constexpr int PER = (kNumSymbols + T - 1) / T;
@@ -338,25 +471,28 @@ __device__ void buildLut(const uint8_t* __restrict__ ans, uint32_t* __restrict__
   for (uint32_t sym = warp; sym < kNumSymbols; sym += WARPS) {
     const uint32_t pdf = sPdf[sym], begin = sCdf[sym];
     for (uint32_t j = lane; j < pdf; j += 32u) {
-      if (begin + j < (1u << PB)) lut[begin + j] = (pdf << 20) | (j << 8) | sym;
+      if (begin + j < (1u << PB)) lut[begin + j] = Lut<PB, LUT64>::make(pdf, j, sym);
     }
   }
   __syncthreads();
 }
 
-template <int KIND, int PB, int WARPS, bool STAGE>
-__global__ void __launch_bounds__(WARPS * 32)
-decodeKernel(DecodeScratch sc, uint32_t n) {
+template <int KIND, int PB, int WARPS, bool STAGE, bool LUT64>
+__global__ void __launch_bounds__(WARPS * 32, DGB_DECODE_WARPS_PER_SM / WARPS)
+decodeKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t K = 1u << PB;
-  constexpr uint32_t slotBytes = 128u + maxBlockWords(PB) * 2u;  // lane states + stream
-  __shared__ __align__(16) uint32_t lut[K];  // static: constant base address for the hot LDS
+  typedef typename Lut<PB, LUT64>::Entry Entry;
+  __shared__ __align__(16) Entry lut[K];  // static: constant base address for the hot LDS
   uint32_t* sPdf = reinterpret_cast<uint32_t*>(smem);
   uint32_t* sCdf = sPdf + kNumSymbols;
   uint32_t* sWarp = sCdf + kNumSymbols;           // 32 words
   uint32_t* sMisc = sWarp + 32;                   // 32 words
   unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sMisc + 32);  // [WARPS]
-  uint8_t* sSlots = reinterpret_cast<uint8_t*>(sBar + ((WARPS + 1) & ~1));
+  uint8_t* sRing = reinterpret_cast<uint8_t*>(sBar + ((WARPS + 1) & ~1));  // [WARPS] stored-byte rings
+  constexpr uint32_t ringBytes = kRingSlots * RowWriter<KIND>::kRingSlotBytes;
+  uint8_t* sSlots = sRing + WARPS * ringBytes;
+  const uint32_t slotBytes = 128u + slotWords * 2u;  // lane states + stream
 
   const uint32_t t = threadIdx.x, lane = t & 31u;
   // shuffle makes the warp index provably warp-uniform, so the vote in the hot loop needs no
@@ -378,15 +514,14 @@ decodeKernel(DecodeScratch sc, uint32_t n) {
   const uint32_t end = (uint32_t)((uint64_t)total * (blockIdx.x + 1) / g);
 
   while (cur < end) {
-    // member containing flat block `cur`
+    // member containing flat block `cur`: the last member whose first block <= cur (members
+    // that contribute no blocks share their successor's start and are skipped by the search)
     if (t == 0) {
       uint32_t lo = 0, hi = n;
       while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (__ldcg(&sc.members[mid].work0) <= cur) lo = mid; else hi = mid;
       }
-      // skip members that contribute no blocks (failed / empty): the search lands on the
-      // last member whose start <= cur, which is the one owning `cur`
       sMisc[0] = lo;
     }
     __syncthreads();
@@ -397,7 +532,7 @@ decodeKernel(DecodeScratch sc, uint32_t n) {
     const uint32_t nb = h0.y;
     const uint32_t memberFirst = __ldcg(&sc.members[m].work0);
     const uint32_t memberEnd = min(end, memberFirst + nb);
-    buildLut<PB, WARPS>(av.ans, lut, sPdf, sCdf, sWarp);
+    buildLut<PB, LUT64, WARPS>(av.ans, lut, sPdf, sCdf, sWarp);
 
     const uint8_t* pStates = av.ans + kAnsHeaderBytes + kAnsPdfBytes;
     const uint2* pBlockWords = reinterpret_cast<const uint2*>(pStates + 128u * (size_t)nb);
@@ -406,15 +541,15 @@ decodeKernel(DecodeScratch sc, uint32_t n) {
     const bool canStage = STAGE && ((reinterpret_cast<uintptr_t>(av.ans) & 15u) == 0);
 
     RowWriter<KIND> wr;
+    wr.setRing(smemAddr(sRing + warp * ringBytes), lane);
     for (uint32_t fb = cur + warp; fb < memberEnd; fb += WARPS) {
       const uint32_t block = fb - memberFirst;
       const uint2 bw = __ldg(pBlockWords + block);
       const uint32_t blockLen = bw.x >> 16, words = bw.x & 0xffffu;
       const uint16_t* stream = pData + bw.y;
       wr.setBlock(av, md.out, block, lane);
-      // two call sites on purpose: the compiler then knows the address space of the stream
-      // (LDS for the staged copy, LDG for the direct path) instead of a generic pointer
-      if (canStage && words <= maxBlockWords(PB) && (bw.y & 7u) == 0u) {
+      // two call sites on purpose: each knows the address space of the stream
+      if (canStage && words <= slotWords && (bw.y & 7u) == 0u) {
         const uint32_t streamBytes = roundUp(words, 8u) * 2u;
         __syncwarp();
         if (lane == 0) {
@@ -425,11 +560,12 @@ decodeKernel(DecodeScratch sc, uint32_t n) {
         mbarWait(myBar, phase);
         phase ^= 1u;
         const uint32_t state = reinterpret_cast<const uint32_t*>(mySlot)[lane];
-        decodeBlockWarp<KIND, PB>(state, reinterpret_cast<const uint16_t*>(mySlot + 128) + words,
-                                  blockLen, lut, wr, lane);
+        SmemStream st{smemAddr(mySlot + 128) + 2u * words};
+        decodeBlockWarp<KIND, PB, LUT64>(state, st, blockLen, lut, wr, lane);
       } else {
         const uint32_t state = __ldg(reinterpret_cast<const uint32_t*>(pStates) + block * 32u + lane);
-        decodeBlockWarp<KIND, PB>(state, stream + words, blockLen, lut, wr, lane);
+        GmemStream st{stream + words};
+        decodeBlockWarp<KIND, PB, LUT64>(state, st, blockLen, lut, wr, lane);
       }
     }
     cur = memberEnd;
@@ -481,49 +617,71 @@ int smCountD() {
   return cached;
 }
 
-template <int KIND, int PB, int WARPS, bool STAGE>
+template <int KIND, int PB, int WARPS, bool STAGE, bool LUT64>
 int launchDecode(const DecodeScratch& sc, uint32_t n, uint64_t blockBound, cudaStream_t stream) {
-  auto kern = decodeKernel<KIND, PB, WARPS, STAGE>;
-  constexpr uint32_t K = 1u << PB;
-  size_t smemBytes = (2 * kNumSymbols + 64) * 4 + ((WARPS + 1) & ~1) * 8;
-  (void)K;
-  if (STAGE) smemBytes += (size_t)WARPS * (128u + maxBlockWords(PB) * 2u);
+  auto kern = decodeKernel<KIND, PB, WARPS, STAGE, LUT64>;
+  const Options& opt = options();
+  // staging slot per warp: worst case for raw bytes; float kinds code exponent-like bytes that
+  // compress well, so a smaller slot (more resident warps) covers them and rare larger blocks
+  // take the direct-from-global path inside the kernel
+  uint32_t slotWords = 0;
+  if (STAGE) {
+    slotWords = opt.decode_slot_words > 0 ? (uint32_t)opt.decode_slot_words
+                                          : (KIND == kKindBytes ? maxBlockWords(PB) : 1536u);
+    slotWords = std::min(roundUp(slotWords, 8u), maxBlockWords(PB));
+  }
+  size_t smemBytes = (2 * kNumSymbols + 64) * 4 + ((WARPS + 1) & ~1) * 8 +
+                     (size_t)WARPS * kRingSlots * RowWriter<KIND>::kRingSlotBytes;
+  if (STAGE) smemBytes += (size_t)WARPS * (128u + slotWords * 2u);
   static int perSm = 0;  // per instantiation; one device per process (one rank per GPU)
-  if (perSm == 0) {
-    DGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  static size_t perSmKey = 0;
+  if (perSm == 0 || perSmKey != smemBytes) {
+    DGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int occ = 0;
     DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smemBytes));
     perSm = std::max(occ, 1);
+    perSmKey = smemBytes;
   }
-  const uint64_t want = (blockBound + WARPS - 1) / WARPS;
-  const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)perSm * smCountD()));
-  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, n);
+  // one resident wave; every warp gets the same number of blocks (rounds) when the batch is
+  // large, so no warp idles at the CTA barrier waiting for a neighbour's extra block
+  const uint64_t resident = (uint64_t)perSm * smCountD();
+  const uint64_t rounds = std::max<uint64_t>(1, (blockBound + resident * WARPS - 1) / (resident * WARPS));
+  const uint64_t want = (blockBound + WARPS * rounds - 1) / (WARPS * rounds);
+  const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
+  timerBegin(kSlotDecode, stream);
+  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, n, slotWords);
   DGB_CUDA_TRY(cudaGetLastError());
+  timerEnd(kSlotDecode, stream);
   return DGB_OK;
+}
+
+template <int KIND, int PB, int WARPS>
+int launchDecodeV(const DecodeScratch& sc, uint32_t n, uint64_t blockBound, cudaStream_t stream) {
+  const Options& opt = options();
+  const bool stage = opt.decode_stage != 0, l64 = opt.decode_lut64 != 0;
+  if (stage) {
+    return l64 ? launchDecode<KIND, PB, WARPS, true, true>(sc, n, blockBound, stream)
+               : launchDecode<KIND, PB, WARPS, true, false>(sc, n, blockBound, stream);
+  }
+  return l64 ? launchDecode<KIND, PB, WARPS, false, true>(sc, n, blockBound, stream)
+             : launchDecode<KIND, PB, WARPS, false, false>(sc, n, blockBound, stream);
 }
 
 template <int KIND, int PB>
 int launchDecodeW(const DecodeScratch& sc, uint32_t n, uint64_t blockBound, cudaStream_t stream) {
-  const Options& opt = options();
-  const bool stage = opt.decode_stage != 0;
-  switch (opt.decode_warps) {
-    case 2:
-      return stage ? launchDecode<KIND, PB, 2, true>(sc, n, blockBound, stream)
-                   : launchDecode<KIND, PB, 2, false>(sc, n, blockBound, stream);
-    case 8:
-      return stage ? launchDecode<KIND, PB, 8, true>(sc, n, blockBound, stream)
-                   : launchDecode<KIND, PB, 8, false>(sc, n, blockBound, stream);
-    default:
-      return stage ? launchDecode<KIND, PB, 4, true>(sc, n, blockBound, stream)
-                   : launchDecode<KIND, PB, 4, false>(sc, n, blockBound, stream);
+  switch (options().decode_warps) {
+    case 8: return launchDecodeV<KIND, PB, 8>(sc, n, blockBound, stream);
+    default: return launchDecodeV<KIND, PB, 4>(sc, n, blockBound, stream);
   }
 }
 
 template <int KIND>
 int decodeKind(const DecodeScratch& sc, int pb, bool checksum, uint32_t n, uint64_t blockBound,
                uint8_t* outSuccess, uint32_t* outSize, cudaStream_t stream) {
+  timerBegin(kSlotPlan, stream);
   planKernel<KIND><<<1, 1024, 0, stream>>>(sc, n, pb, outSuccess, outSize, checksum);
   DGB_CUDA_TRY(cudaGetLastError());
+  timerEnd(kSlotPlan, stream);
   switch (pb) {
     case 9: return launchDecodeW<KIND, 9>(sc, n, blockBound, stream);
     case 10: return launchDecodeW<KIND, 10>(sc, n, blockBound, stream);

@@ -748,6 +748,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   const uint32_t wantY = std::max(1u, (uint32_t)(8 * sms * 4) / n);
   gridY = std::min(std::min(gridY, wantY), 65535u);
   dim3 grid1(n, gridY);
+  timerBegin(kSlotStats, stream);
   if (kind == kKindBytes) {
     statsBytesKernel<<<grid1, kStatsThreads, 0, stream>>>(sc, histogram_dev, pb, checksum, slabVecs,
                                                           outSize_dev);
@@ -759,6 +760,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     statsFloatKernel<DGB_FLOAT32><<<grid1, kStatsThreads, 0, stream>>>(sc, pb, checksum, slabVecs, outSize_dev);
   }
   DGB_CUDA_TRY(cudaGetLastError());
+  timerEnd(kSlotStats, stream);
 
   // ---- K2 ----
   if (totalTickets > 0) {
@@ -781,9 +783,11 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
       occKeyW = W;
     }
     const uint32_t grid2 = std::min<uint32_t>(totalTickets, (uint32_t)(perSm * sms));
+    timerBegin(kSlotEncode, stream);
     encodeKernel<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, (int)W,
                                                       outSize_dev);
     DGB_CUDA_TRY(cudaGetLastError());
+    timerEnd(kSlotEncode, stream);
   }
   return DGB_OK;
 }

@@ -1,0 +1,126 @@
+"""GPU parity against the REFERENCE ITSELF: facebookresearch/dietgpu compiled unmodified for
+sm_100a into oracle/_ref/ (oracle/build_ref.sh).  Pins what the reference's own tests leave
+unpinned: byte-exact compressed sizes, field-exact archives (masking only the bits
+the reference leaves undefined), and cross-decoding in both directions."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import exp_bytes, normal_words, zipf_bytes
+from oracle import oracle as O
+from oracle import ref_lib
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not built")]
+
+KINDS = {"f16": (1, torch.float16), "bf16": (2, torch.bfloat16), "f32": (3, torch.float32)}
+
+
+def dg():
+    import dietgpu_b200
+
+    return dietgpu_b200
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_lib.RefCodec(512 << 20)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def assert_same_ans(mine: np.ndarray, theirs: np.ndarray):
+    a, b = O.parse_ans(mine), O.parse_ans(theirs)
+    for k in ("magic", "num_blocks", "uncompressed", "total_words", "prob_bits", "size"):
+        assert a[k] == b[k], k
+    assert np.array_equal(a["pdf"], b["pdf"])
+    assert np.array_equal(a["states"], b["states"])
+    assert np.array_equal(a["block_words"], b["block_words"])
+    for x, y in zip(a["streams"], b["streams"]):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("pb", [9, 10, 11])
+def test_ans_matches_reference(ref, pb):
+    arrays = [exp_bytes(10013, 10, 1), zipf_bytes(300000, 1.0, 2), exp_bytes(4096, 100, 3), exp_bytes(1, 1, 4),
+              np.random.default_rng(5).integers(100, 160, 30000).astype(np.uint8),  # 'add' branch by symbol id
+              np.random.default_rng(6).integers(0, 256, 70000, dtype=np.uint8)]
+    ts = [dev(a) for a in arrays]
+    n = len(ts)
+    comp, sizes, _ = dg().compress_data(False, ts, True, prob_bits=pb)
+    cols = ref_lib.lib().ref_ans_max_compressed_size(max(a.size for a in arrays))
+    assert cols == comp.size(1)
+    rcomp = torch.zeros((n, cols), dtype=torch.uint8, device="cuda")
+    rsizes = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ref.ans_encode(ts, rcomp, rsizes, pb, True)
+    torch.cuda.synchronize()
+    hs, rs = sizes.cpu().tolist(), rsizes.cpu().tolist()
+    assert hs == rs, "compressed sizes differ from the reference"
+    for i in range(n):
+        mine, theirs = comp[i, :hs[i]].cpu().numpy(), rcomp[i, :rs[i]].cpu().numpy()
+        assert_same_ans(mine, theirs)
+        assert np.array_equal(mine, O.ans_encode(arrays[i], pb, True))
+    # cross decode: ours <- reference archives, reference <- our archives
+    outs = [torch.empty_like(t) for t in ts]
+    dg().decompress_data(False, [rcomp[i, :rs[i]] for i in range(n)], outs, True, prob_bits=pb)
+    for t, o in zip(ts, outs):
+        assert torch.equal(t, o)
+    outs = [torch.zeros_like(t) for t in ts]
+    st = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    assert ref.ans_decode([comp[i, :hs[i]].clone() for i in range(n)], outs, st, None, pb, True) == 0
+    torch.cuda.synchronize()
+    assert st.cpu().tolist() == [1] * n
+    for t, o in zip(ts, outs):
+        assert torch.equal(t, o)
+
+
+@pytest.mark.parametrize("kind", ["f16", "bf16", "f32"])
+def test_float_matches_reference(ref, kind):
+    ft, tdt = KINDS[kind]
+    words = [normal_words(n, kind, 20 + i) for i, n in enumerate((10000, 123457, 4096, 1, 524288))]
+    it = torch.int16 if kind != "f32" else torch.int32
+    ts = [torch.from_numpy(w.view(np.int16 if kind != "f32" else np.int32).copy()).view(tdt).cuda() for w in words]
+    n = len(ts)
+    comp, sizes, _ = dg().compress_data(True, ts, True)
+    cols = ref_lib.lib().ref_float_max_compressed_size(ft, max(w.size for w in words))
+    assert cols == comp.size(1)
+    rcomp = torch.zeros((n, cols), dtype=torch.uint8, device="cuda")
+    rsizes = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ref.float_compress(ft, ts, rcomp, rsizes, 10, True)
+    torch.cuda.synchronize()
+    hs, rs = sizes.cpu().tolist(), rsizes.cpu().tolist()
+    assert hs == rs, "float compressed sizes differ from the reference"
+    for i, w in enumerate(words):
+        mine, theirs = comp[i, :hs[i]].cpu().numpy(), rcomp[i, :rs[i]].cpu().numpy()
+        nc = O.float_noncomp_bytes(ft, w.size)
+        # float header: magic, size, type|checksum flag, checksum
+        assert np.array_equal(mine[:8], theirs[:8])
+        assert (mine[8] & 0x1f) == (theirs[8] & 0x1f) and np.array_equal(mine[12:16], theirs[12:16])
+        # stored planes: compare the defined bytes only (padding is undefined in the reference)
+        if kind == "f32":
+            assert np.array_equal(mine[16:16 + 2 * w.size], theirs[16:16 + 2 * w.size])
+            o1 = 16 + 2 * ((w.size + 7) // 8 * 8)
+            assert np.array_equal(mine[o1:o1 + w.size], theirs[o1:o1 + w.size])
+        else:
+            assert np.array_equal(mine[16:16 + w.size], theirs[16:16 + w.size])
+        assert_same_ans(mine[16 + nc:], theirs[16 + nc:])
+    outs = [torch.empty_like(t) for t in ts]
+    dg().decompress_data(True, [rcomp[i, :rs[i]] for i in range(n)], outs, True)
+    for t, o in zip(ts, outs):
+        assert torch.equal(t.view(it), o.view(it))
+    outs = [torch.zeros_like(t) for t in ts]
+    st = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    assert ref.float_decompress(ft, [comp[i, :hs[i]].clone() for i in range(n)], outs, st, None, 10, True) == 0
+    torch.cuda.synchronize()
+    assert st.cpu().tolist() == [1] * n
+    for t, o in zip(ts, outs):
+        assert torch.equal(t.view(it), o.view(it))
+
+
+def test_max_sizes_match_reference():
+    L, R = dg().capi.lib(), ref_lib.lib()
+    for n in (0, 1, 4095, 4096, 4097, 1 << 20, 4 << 20, 123456789, 0x7fffffff // 2):
+        assert L.dgb_ans_max_compressed_size(n) == R.ref_ans_max_compressed_size(n)
+        for ft in (1, 2, 3):
+            assert L.dgb_float_max_compressed_size(ft, n) == R.ref_float_max_compressed_size(ft, n)
