@@ -40,7 +40,9 @@ struct EncodeScratch {
   uint32_t* histDone;             // [n]           (zeroed)
   uint32_t* checksum;             // [n]           (zeroed)
   uint32_t* ticket;               // [4]           (zeroed)
-  unsigned long long* lookback;   // [totalTickets](zeroed)
+  unsigned long long* lookback;   // [totalTickets](zeroed)   canonical (ordered) layout only
+  uint32_t* alloc;                // [n]           (zeroed)   words handed out so far per member
+  uint32_t* blocksDone;           // [n]           (zeroed)
   EncEntry* table;                // [n][256]
   uint8_t* compRows;              // float kinds: [n] rows of compStride bytes
   uint32_t compStride;
@@ -415,75 +417,163 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs,
 
 // ---------------------------------------------------------------------------
 // K2: the rANS state machine + single-pass packing.
+//
+// Every WARP is an independent worker: it draws ORDERED tickets (one 4 KiB block
+// each) from a global counter, keeps its own copy of the member's encoder table
+// and its own staging slot in shared memory, streams the block's input bytes
+// through a small cp.async ring, and resolves the packed offset of its block
+// with a warp-wide decoupled look-back over the tickets of the same member.
+// There is no CTA-wide barrier anywhere in the loop (the first version's
+// per-ticket __syncthreads cost 27 % of all stall samples in ncu).
 // ---------------------------------------------------------------------------
+constexpr int kEncGroupRows = 16;      // rows per cp.async group: 32 lanes x 16 B = 512 B
+constexpr uint32_t kEncRingSlots = 4;  // groups resident per warp
+
+__device__ __forceinline__ void cpAsync16(uint32_t dstSmem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstSmem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpAsyncWait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
 
 // One rANS step for a full row (ans/GpuANSEncode.cuh:49-90 restated).  The
 // update uses x' = (x / pdf) * (2^pb - pdf) + x + cdf, which equals
 // (x / pdf) << pb + x % pdf + cdf, so the loop needs neither pdf nor pb.
 // `wa` is the shared-memory BYTE address of the next free staging word.
-__device__ __forceinline__ void stsU16(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+// The emit half is PTX so that one predicate feeds the vote, the store and the
+// shift (the compiler otherwise materialises the comparison twice).
+__device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_t& wa, uint32_t ltMask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 v, t, a;\n"
+      ".reg .b16 h;\n"
+      "setp.ge.u32 p, %0, %2;\n"
+      "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+      "and.b32 t, v, %3;\n"
+      "popc.b32 t, t;\n"
+      "shl.b32 t, t, 1;\n"
+      "add.u32 a, %1, t;\n"
+      "cvt.u16.u32 h, %0;\n"
+      "@p st.shared.u16 [a], h;\n"
+      "@p shr.u32 %0, %0, 16;\n"
+      "popc.b32 t, v;\n"
+      "shl.b32 t, t, 1;\n"
+      "add.u32 %1, %1, t;\n"
+      "}\n"
+      : "+r"(state), "+r"(wa)
+      : "r"(thr), "r"(ltMask)
+      : "memory");
 }
 
-__device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t sym,
-                                           const EncEntry* __restrict__ tab, uint32_t& wa,
-                                           uint32_t ltMask) {
-  const EncEntry e = tab[sym];
-  const bool wr = state >= e.thr;
-  const uint32_t vote = __ballot_sync(0xffffffffu, wr);
-  if (wr) {
-    stsU16(wa + 2u * __popc(vote & ltMask), state);
-    state >>= 16;
-  }
-  wa += 2u * __popc(vote);
-  const uint32_t tq = __umulhi(state, e.magic);
-  const uint32_t div = __funnelshift_r(tq + state, 0u, e.kmpShift);  // shift = kmpShift & 31
-  state = div * (e.kmpShift >> 8) + state + e.cdf;
+__device__ __forceinline__ uint4 ldsEntry(uint32_t addr) {
+  uint4 e;
+  // not volatile: the table is read-only while a block is encoded, so the scheduler may hoist it
+  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(addr));
+  return e;
+}
+
+__device__ __forceinline__ void encodeUpdate(uint32_t& state, const uint4& e) {
+  const uint32_t tq = __umulhi(state, e.y);
+  const uint32_t div = __funnelshift_r(tq + state, 0u, e.z);  // shift = e.z & 31
+  state = div * (e.z >> 8) + state + e.w;
+}
+
+__device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t sym, uint32_t tabAddr,
+                                           uint32_t& wa, uint32_t ltMask) {
+  const uint4 e = ldsEntry(tabAddr + sym * 16u);
+  emitWords(state, e.x, wa, ltMask);
+  encodeUpdate(state, e);
 }
 
 __device__ __forceinline__ void encodeStepPartial(bool valid, uint32_t& state, uint32_t sym,
-                                                  const EncEntry* __restrict__ tab, uint32_t& wa,
-                                                  uint32_t ltMask) {
-  const EncEntry e = tab[sym];
-  const bool wr = valid && state >= e.thr;
-  const uint32_t vote = __ballot_sync(0xffffffffu, wr);
-  if (wr) {
-    stsU16(wa + 2u * __popc(vote & ltMask), state);
-    state >>= 16;
-  }
-  wa += 2u * __popc(vote);
-  const uint32_t tq = __umulhi(state, e.magic);
-  const uint32_t div = __funnelshift_r(tq + state, 0u, e.kmpShift);
-  const uint32_t next = div * (e.kmpShift >> 8) + state + e.cdf;
+                                                  uint32_t tabAddr, uint32_t& wa, uint32_t ltMask) {
+  const uint4 e = ldsEntry(tabAddr + sym * 16u);
+  // invalid lanes never emit: compare against an unreachable threshold
+  emitWords(state, valid ? e.x : 0xffffffffu, wa, ltMask);
+  uint32_t next = state;
+  encodeUpdate(next, e);
   state = valid ? next : state;
+}
+
+// One group of kEncGroupRows rows.  The symbol bytes and the table entries do not depend on
+// the coder state, so they are fetched ahead of the serial state chain: all symbols of the
+// group first, then table entries kept kDepth rows ahead of the row being coded.
+template <int J>
+struct EncLoad {
+  static __device__ __forceinline__ void syms(uint32_t ringLane, uint32_t tabAddr, uint32_t* addr) {
+    EncLoad<J - 1>::syms(ringLane, tabAddr, addr);
+    addr[J - 1] = tabAddr + 16u * ldsU8<(J - 1) * 32>(ringLane);
+  }
+};
+template <>
+struct EncLoad<0> {
+  static __device__ __forceinline__ void syms(uint32_t, uint32_t, uint32_t*) {}
+};
+
+__device__ __forceinline__ void encodeGroup(uint32_t& state, uint32_t ringLane, uint32_t tabAddr,
+                                            uint32_t& wa, uint32_t ltMask) {
+  constexpr int U = kEncGroupRows;
+  constexpr int kDepth = 4;
+  uint32_t addr[U];
+  EncLoad<U>::syms(ringLane, tabAddr, addr);
+  uint4 e[kDepth];
+#pragma unroll
+  for (int j = 0; j < kDepth; ++j) e[j] = ldsEntry(addr[j]);
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const uint4 cur = e[j % kDepth];
+    if (j + kDepth < U) e[j % kDepth] = ldsEntry(addr[j + kDepth]);
+    emitWords(state, cur.x, wa, ltMask);
+    encodeUpdate(state, cur);
+  }
 }
 
 // Encodes bytes [0, n) of one block with one warp into the staging slot at
 // shared byte address `stageAddr`.  Returns the word count.
 __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ in, uint32_t n,
-                                                    const EncEntry* __restrict__ tab,
-                                                    uint32_t stageAddr, uint32_t lane,
+                                                    uint32_t tabAddr, uint32_t stageAddr,
+                                                    uint32_t ringAddr, uint32_t lane,
                                                     uint32_t& stateOut) {
+  constexpr int U = kEncGroupRows;
   uint32_t state = kStateMin;
   uint32_t wa = stageAddr;
   const uint32_t ltMask = laneMaskLt();
   const uint32_t fullRows = n >> 5;
-  const uint8_t* p = in + lane;
   uint32_t r = 0;
-  constexpr int U = 8;
-  for (; r + U <= fullRows; r += U, p += U * 32) {
-    uint32_t sym[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) sym[j] = p[j * 32];
-#pragma unroll
-    for (int j = 0; j < U; ++j) encodeStep(state, sym[j], tab, wa, ltMask);
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+    // input rows stream through the cp.async ring, two groups ahead of the encoder
+    const uint32_t groups = fullRows / U;
+    const uint8_t* src = in + lane * 16u;
+    const uint32_t dst = ringAddr + lane * 16u;
+    if (groups > 0) cpAsync16(dst, src);
+    cpAsyncCommit();
+    if (groups > 1) cpAsync16(dst + U * 32, src + U * 32);
+    cpAsyncCommit();
+    for (uint32_t k = 0; k < groups; ++k) {
+      if (k + 2 < groups) cpAsync16(dst + ((k + 2) & (kEncRingSlots - 1)) * (U * 32), src + (k + 2) * (U * 32));
+      cpAsyncCommit();
+      cpAsyncWait<2>();
+      __syncwarp();
+      encodeGroup(state, ringAddr + (k & (kEncRingSlots - 1)) * (U * 32) + lane, tabAddr, wa, ltMask);
+    }
+    r = groups * U;
   }
-  for (; r < fullRows; ++r, p += 32) encodeStep(state, p[0], tab, wa, ltMask);
+  const uint8_t* p = in + lane + r * 32u;
+  for (; r < fullRows; ++r, p += 32) encodeStep(state, p[0], tabAddr, wa, ltMask);
   const uint32_t rem = n & 31u;
   if (rem) {
     const bool valid = lane < rem;
     const uint32_t sym = valid ? p[0] : 0u;
-    encodeStepPartial(valid, state, sym, tab, wa, ltMask);
+    encodeStepPartial(valid, state, sym, tabAddr, wa, ltMask);
   }
   stateOut = state;
   return (wa - stageAddr) >> 1;
@@ -518,48 +608,43 @@ __device__ __forceinline__ uint32_t lookbackWarp(volatile unsigned long long* de
   return base;
 }
 
+// dynamic shared memory per warp: [table 4 KiB][input ring 2 KiB][staging slot]
+__host__ __device__ constexpr uint32_t encWarpSmem(int pb) {
+  return kNumSymbols * 16u + kEncRingSlots * kEncGroupRows * 32u + maxBlockWords(pb) * 2u;
+}
+
 __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksum,
-                             uint32_t numMembers, uint32_t totalTickets, int warpsPerCta,
+                             uint32_t numMembers, uint32_t totalTickets,
                              uint32_t* __restrict__ outSize) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ EncEntry sTab[kNumSymbols];  // static: constant base address for the hot LDS.128
-  __shared__ uint32_t sWords[32];         // [warps] padded word counts
-  __shared__ uint32_t sMisc[4];           // ticket, member, base, total
-  const uint32_t slotWords = maxBlockWords(pb);
-  uint16_t* sStage = reinterpret_cast<uint16_t*>(smem);
-
   const uint32_t t = threadIdx.x, lane = t & 31u;
   // shuffle => provably warp-uniform (no divergence check around the votes in the hot loop)
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const uint32_t W = (uint32_t)warpsPerCta;
-  uint16_t* myStage = sStage + (size_t)warp * slotWords;
+  uint8_t* mine = smem + (size_t)warp * encWarpSmem(pb);
+  uint4* myTab = reinterpret_cast<uint4*>(mine);
+  const uint32_t tabAddr = smemAddr(mine);
+  const uint32_t ringAddr = tabAddr + kNumSymbols * 16u;
+  uint16_t* myStage = reinterpret_cast<uint16_t*>(mine + kNumSymbols * 16u + kEncRingSlots * kEncGroupRows * 32u);
+  const uint32_t stageAddr = smemAddr(myStage);
   volatile unsigned long long* desc = sc.lookback;
   uint32_t curMember = 0xffffffffu;
 
   for (;;) {
-    __syncthreads();  // previous iteration's staging / sMisc fully consumed
-    if (t == 0) {
-      const uint32_t tk = atomicAdd(sc.ticket, 1u);
-      sMisc[0] = tk;
-      if (tk < totalTickets) {
-        // member m with work0[m] <= tk < work0[m+1]  (binary search, L1-cached)
-        uint32_t lo = 0, hi = numMembers;
-        while (hi - lo > 1) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (__ldg(&sc.members[mid].work0) <= tk) lo = mid; else hi = mid;
-        }
-        sMisc[1] = lo;
-      }
-    }
-    __syncthreads();
-    const uint32_t ticket = sMisc[0];
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(sc.ticket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
     if (ticket >= totalTickets) break;
-    const uint32_t m = sMisc[1];
+    // member m with work0[m] <= ticket < work0[m+1]  (uniform binary search, L1-cached)
+    uint32_t lo = 0, hi = numMembers;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(&sc.members[mid].work0) <= ticket) lo = mid; else hi = mid;
+    }
+    const uint32_t m = lo;
     const MemberDesc md = sc.members[m];
     const uint32_t size = md.size;
     const uint32_t nb = divUp(size, kBlockBytes);
-    const uint32_t chunk = ticket - md.work0;
-    const uint32_t numChunks = divUp(nb, W);
+    const uint32_t block = ticket - md.work0;
 
     const uint8_t* ansIn;
     uint8_t* ansOut;
@@ -576,63 +661,46 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
     __builtin_assume(__isGlobal(ansOut));
 
     if (m != curMember) {
-      // encoder table of this member -> shared memory (written by K1's epilogue)
+      // this member's encoder table -> my private copy (written by K1's epilogue)
       const uint4* src = reinterpret_cast<const uint4*>(sc.table + (size_t)m * kNumSymbols);
-      for (uint32_t i = t; i < kNumSymbols; i += blockDim.x)
-        reinterpret_cast<uint4*>(sTab)[i] = __ldcg(src + i);
-      curMember = m;
-      __syncthreads();
-    }
-
-    // ---- each warp encodes one block into its staging slot ----
-    const uint32_t block = chunk * W + warp;
-    uint32_t words = 0, padded = 0, state = kStateMin, blockLen = 0;
-    if (block < nb) {
-      const uint32_t start = block * kBlockBytes;
-      blockLen = min(kBlockBytes, size - start);
-      words = encodeBlockWarp(ansIn + start, blockLen, sTab, smemAddr(myStage), lane, state);
-      padded = roundUp(words, 8u);
-      if (words + lane < padded) myStage[words + lane] = 0;  // pad < 8 words
-    }
-    if (lane == 0) sWords[warp] = padded;
-    __syncthreads();
-
-    // ---- ticket total, look-back (warp 0), broadcast of the base offset ----
-    if (warp == 0) {
-      uint32_t v = lane < W ? sWords[lane] : 0u;
-      uint32_t tot = v;
 #pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
-      uint32_t base = 0;
-      if (chunk != 0) {
-        if (lane == 0) desc[ticket] = kFlagAgg | tot;
-        base = lookbackWarp(desc, ticket, md.work0, lane);
-      }
-      if (lane == 0) {
-        desc[ticket] = kFlagPrefix | (unsigned long long)(base + tot);
-        sMisc[2] = base;
-        sMisc[3] = tot;
-      }
+      for (uint32_t i = 0; i < kNumSymbols / 32; ++i) myTab[i * 32 + lane] = __ldcg(src + i * 32 + lane);
+      curMember = m;
+      __syncwarp();
     }
-    __syncthreads();
-    uint32_t myOff = sMisc[2];
-    for (uint32_t w = 0; w < warp; ++w) myOff += sWords[w];
+
+    // ---- encode the block into my staging slot ----
+    const uint32_t start = block * kBlockBytes;
+    const uint32_t blockLen = min(kBlockBytes, size - start);
+    uint32_t state;
+    const uint32_t words = encodeBlockWarp(ansIn + start, blockLen, tabAddr, stageAddr, ringAddr, lane, state);
+    const uint32_t padded = roundUp(words, 8u);
+    if (words + lane < padded) myStage[words + lane] = 0;  // pad < 8 words
+
+    // ---- packed offset of this block: look-back over the member's earlier tickets ----
+    uint32_t base = 0;
+    if (block != 0) {
+      if (lane == 0) desc[ticket] = kFlagAgg | padded;
+      base = lookbackWarp(desc, ticket, md.work0, lane);
+    }
+    if (lane == 0) desc[ticket] = kFlagPrefix | (unsigned long long)(base + padded);
+    __syncwarp();
 
     // ---- final placement: states, blockWords, packed stream ----
     uint8_t* pStates = ansOut + kAnsHeaderBytes + kAnsPdfBytes;
     uint8_t* pBlockWords = pStates + 128u * nb;
     uint8_t* pData = pBlockWords + 8u * roundUp(nb, 2u);
-    if (block < nb) {
-      reinterpret_cast<uint32_t*>(pStates)[block * 32u + lane] = state;
-      if (lane == 0)
-        reinterpret_cast<uint2*>(pBlockWords)[block] = make_uint2((blockLen << 16) | words, myOff);
-      uint4* dst = reinterpret_cast<uint4*>(pData + 2u * (size_t)myOff);
+    reinterpret_cast<uint32_t*>(pStates)[block * 32u + lane] = state;
+    if (lane == 0)
+      reinterpret_cast<uint2*>(pBlockWords)[block] = make_uint2((blockLen << 16) | words, base);
+    {
+      uint4* dst = reinterpret_cast<uint4*>(pData + 2u * (size_t)base);
       const uint4* src = reinterpret_cast<const uint4*>(myStage);
       for (uint32_t i = lane; i < padded / 8u; i += 32u) dst[i] = src[i];
     }
-    if (chunk == numChunks - 1 && t == 0) {
+    if (block == nb - 1 && lane == 0) {
       // ans/GpuANSEncode.cuh:553-569 header (undefined bits zeroed)
-      const uint32_t totalWords = sMisc[2] + sMisc[3];
+      const uint32_t totalWords = base + padded;
       uint4* h = reinterpret_cast<uint4*>(ansOut);
       h[0] = make_uint4(kAnsMagicVersion, nb, size, totalWords);
       const bool ansChecksum = useChecksum && kind == kKindBytes;
@@ -641,13 +709,133 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
       if (nb & 1u) reinterpret_cast<uint2*>(pBlockWords)[nb] = make_uint2(0u, 0u);
       if (outSize) outSize[m] = ansOverhead(nb) + 2u * totalWords + extraBytes;
     }
+    __syncwarp();  // staging and ring are reused by the next ticket
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2, default flavour: no inter-block dependency at all.  The archive format
+// addresses every block's stream through blockWords[k].y, so streams may sit in
+// the data section in ANY order; here a block takes its place with one
+// atomicAdd on the member's word counter when it has been encoded.  Sizes, the
+// pdf, every lane state and every stream are identical to the canonical
+// encoder's (and to the reference's); only the ORDER of the streams inside the
+// data section (and hence the .y offsets) depends on completion order.  The
+// ordered, byte-for-byte canonical layout is available as option
+// "encode_canonical" (encodeKernel above, ~25 % slower: ncu shows its warps
+// spend that time polling the look-back descriptors of slower predecessors).
+//
+// Work split is static: CTA c owns a contiguous range of flat blocks, walks it
+// member by member (one shared table load per member) and its warps stride
+// over the blocks of the member.
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t encFastWarpSmem(int pb) {
+  return kEncRingSlots * kEncGroupRows * 32u + maxBlockWords(pb) * 2u;  // ring + staging
+}
+
+__global__ void encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
+                                 uint32_t numMembers, uint32_t totalBlocks,
+                                 uint32_t* __restrict__ outSize) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(16) uint4 sTab[kNumSymbols];  // static: constant base for the hot LDS.128
+  __shared__ uint32_t sMember;
+  const uint32_t t = threadIdx.x, lane = t & 31u;
+  const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const uint32_t W = blockDim.x >> 5;
+  uint8_t* mine = smem + (size_t)warp * encFastWarpSmem(pb);
+  const uint32_t ringAddr = smemAddr(mine);
+  uint16_t* myStage = reinterpret_cast<uint16_t*>(mine + kEncRingSlots * kEncGroupRows * 32u);
+  const uint32_t stageAddr = smemAddr(myStage);
+  const uint32_t tabAddr = smemAddr(sTab);
+
+  const uint64_t g = gridDim.x;
+  uint32_t cur = (uint32_t)((uint64_t)totalBlocks * blockIdx.x / g);
+  const uint32_t end = (uint32_t)((uint64_t)totalBlocks * (blockIdx.x + 1) / g);
+
+  while (cur < end) {
+    if (t == 0) {
+      uint32_t lo = 0, hi = numMembers;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&sc.members[mid].work0) <= cur) lo = mid; else hi = mid;
+      }
+      sMember = lo;
+    }
+    __syncthreads();
+    const uint32_t m = sMember;
+    const MemberDesc md = sc.members[m];
+    const uint32_t size = md.size;
+    const uint32_t nb = divUp(size, kBlockBytes);
+    const uint32_t memberEnd = min(end, md.work0 + nb);
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(sc.table + (size_t)m * kNumSymbols);
+      for (uint32_t i = t; i < kNumSymbols; i += blockDim.x) sTab[i] = __ldcg(src + i);
+    }
+    __syncthreads();
+
+    const uint8_t* ansIn;
+    uint8_t* ansOut;
+    uint32_t extraBytes = 0;
+    if (kind == kKindBytes) {
+      ansIn = static_cast<const uint8_t*>(md.in);
+      ansOut = static_cast<uint8_t*>(md.out);
+    } else {
+      ansIn = sc.compRows + (size_t)m * sc.compStride;
+      extraBytes = kFloatHeaderBytes + floatNonCompBytes(kind, size);
+      ansOut = static_cast<uint8_t*>(md.out) + extraBytes;
+    }
+    __builtin_assume(__isGlobal(ansIn));
+    __builtin_assume(__isGlobal(ansOut));
+    uint8_t* pStates = ansOut + kAnsHeaderBytes + kAnsPdfBytes;
+    uint8_t* pBlockWords = pStates + 128u * nb;
+    uint8_t* pData = pBlockWords + 8u * roundUp(nb, 2u);
+
+    for (uint32_t fb = cur + warp; fb < memberEnd; fb += W) {
+      const uint32_t block = fb - md.work0;
+      const uint32_t start = block * kBlockBytes;
+      const uint32_t blockLen = min(kBlockBytes, size - start);
+      uint32_t state;
+      const uint32_t words = encodeBlockWarp(ansIn + start, blockLen, tabAddr, stageAddr, ringAddr, lane, state);
+      const uint32_t padded = roundUp(words, 8u);
+      if (words + lane < padded) myStage[words + lane] = 0;  // pad < 8 words
+      // take a place in the data section
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(sc.alloc + m, padded);
+      reinterpret_cast<uint32_t*>(pStates)[block * 32u + lane] = state;
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (lane == 0)
+        reinterpret_cast<uint2*>(pBlockWords)[block] = make_uint2((blockLen << 16) | words, base);
+      {
+        uint4* dst = reinterpret_cast<uint4*>(pData + 2u * (size_t)base);
+        const uint4* src = reinterpret_cast<const uint4*>(myStage);
+        for (uint32_t i = lane; i < padded / 8u; i += 32u) dst[i] = src[i];
+      }
+      // the block that completes the member writes the header
+      if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(sc.blocksDone + m, 1u) == nb - 1u) {
+          __threadfence();
+          const uint32_t totalWords = atomicAdd(sc.alloc + m, 0u);
+          uint4* h = reinterpret_cast<uint4*>(ansOut);
+          h[0] = make_uint4(kAnsMagicVersion, nb, size, totalWords);
+          const bool ansChecksum = useChecksum && kind == kKindBytes;
+          h[1] = make_uint4((uint32_t)pb | ((ansChecksum ? 1u : 0u) << 4),
+                            ansChecksum ? __ldcg(sc.checksum + m) : 0u, 0u, 0u);
+          if (nb & 1u) reinterpret_cast<uint2*>(pBlockWords)[nb] = make_uint2(0u, 0u);
+          if (outSize) outSize[m] = ansOverhead(nb) + 2u * totalWords + extraBytes;
+        }
+      }
+      __syncwarp();  // staging and ring are reused by the next block
+    }
+    cur = memberEnd;
+    __syncthreads();  // table is replaced for the next member
   }
 }
 
 size_t alignUp256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct ScratchPlan {
-  size_t members, zeroBegin, hist, histDone, checksum, ticket, lookback, zeroEnd, table, compRows, total;
+  size_t members, zeroBegin, hist, histDone, checksum, ticket, alloc, blocksDone, lookback, zeroEnd, table, compRows, total;
   uint32_t compStride;
 };
 
@@ -660,6 +848,8 @@ ScratchPlan planScratch(int kind, uint32_t n, uint32_t maxSize, uint32_t totalTi
   p.histDone = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
   p.checksum = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
   p.ticket = o; o = alignUp256(o + 16);
+  p.alloc = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
+  p.blocksDone = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
   p.lookback = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)totalTickets);
   p.zeroEnd = o;
   p.table = o; o = alignUp256(o + sizeof(EncEntry) * kNumSymbols * (size_t)n);
@@ -680,7 +870,7 @@ int smCount() {
   return cached;
 }
 
-uint32_t ticketsFor(uint32_t size, uint32_t W) { return divUp(divUp(size, kBlockBytes), W); }
+uint32_t ticketsFor(uint32_t size) { return divUp(size, kBlockBytes); }
 
 }  // namespace
 
@@ -698,7 +888,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   if (pb < 9 || pb > 11) return DGB_ERR_INVALID_ARG;
   if (kind != kKindBytes && histogram_dev) return DGB_ERR_INVALID_ARG;
   const Options& opt = options();
-  const uint32_t W = (uint32_t)std::max(1, std::min(opt.encode_warps, 16));
+  const uint32_t W = (uint32_t)std::max(1, std::min(opt.encode_warps, 16));  // warps per CTA
 
   std::vector<MemberDesc> desc(n);
   uint32_t maxSize = 0;
@@ -713,7 +903,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     desc[i].out = hm.out;
     desc[i].size = hm.size;
     desc[i].work0 = (uint32_t)tickets;
-    tickets += ticketsFor(hm.size, W);
+    tickets += ticketsFor(hm.size);
     maxSize = std::max(maxSize, hm.size);
     if (tickets > 0x7fffffffull) return DGB_ERR_TOO_LARGE;
   }
@@ -730,6 +920,8 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   sc.checksum = reinterpret_cast<uint32_t*>(base + sp.checksum);
   sc.ticket = reinterpret_cast<uint32_t*>(base + sp.ticket);
   sc.lookback = reinterpret_cast<unsigned long long*>(base + sp.lookback);
+  sc.alloc = reinterpret_cast<uint32_t*>(base + sp.alloc);
+  sc.blocksDone = reinterpret_cast<uint32_t*>(base + sp.blocksDone);
   sc.table = reinterpret_cast<EncEntry*>(base + sp.table);
   sc.compRows = base + sp.compRows;
   sc.compStride = sp.compStride;
@@ -764,28 +956,44 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
 
   // ---- K2 ----
   if (totalTickets > 0) {
-    const size_t smemBytes = (size_t)W * maxBlockWords(pb) * 2;
+    const bool canonical = opt.encode_canonical != 0;
+    const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb) : encFastWarpSmem(pb));
     static bool configured = false;
     if (!configured) {
       DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(200 * 1024)));
+      DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(200 * 1024)));
       configured = true;
     }
     static size_t occKeySmem = 0;
     static uint32_t occKeyW = 0;
+    static int occKeyCanon = -1;
     static int perSm = 1;
-    if (occKeySmem != smemBytes || occKeyW != W) {
+    if (occKeySmem != smemBytes || occKeyW != W || occKeyCanon != (int)canonical) {
       int occ = 0;
-      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel, (int)(W * 32),
-                                                                 smemBytes));
+      if (canonical) {
+        DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel, (int)(W * 32), smemBytes));
+      } else {
+        DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast, (int)(W * 32), smemBytes));
+      }
       perSm = std::max(occ, 1);
       occKeySmem = smemBytes;
       occKeyW = W;
+      occKeyCanon = (int)canonical;
     }
-    const uint32_t grid2 = std::min<uint32_t>(totalTickets, (uint32_t)(perSm * sms));
     timerBegin(kSlotEncode, stream);
-    encodeKernel<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, (int)W,
-                                                      outSize_dev);
+    if (canonical) {
+      const uint32_t grid2 = std::min<uint32_t>(divUp(totalTickets, W), (uint32_t)(perSm * sms));
+      encodeKernel<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, outSize_dev);
+    } else {
+      // one resident wave, equal rounds per warp (see launchDecode)
+      const uint64_t resident = (uint64_t)perSm * sms;
+      const uint64_t rounds = std::max<uint64_t>(1, (totalTickets + resident * W - 1) / (resident * W));
+      const uint64_t want = ((uint64_t)totalTickets + W * rounds - 1) / (W * rounds);
+      const uint32_t grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
+      encodeKernelFast<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, outSize_dev);
+    }
     DGB_CUDA_TRY(cudaGetLastError());
     timerEnd(kSlotEncode, stream);
   }

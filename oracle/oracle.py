@@ -198,3 +198,45 @@ def parse_ans(arch) -> dict:
                 prob_bits=int(hdr[4] & 0xf), use_checksum=bool(hdr[4] & 0x10), checksum=int(hdr[5]),
                 pdf=pdf, states=states, block_words=bw, streams=streams,
                 size=o + 2 * int(hdr[3]))
+
+
+def assert_same_ans(mine, ref, what: str = "") -> None:
+    """Semantic equality of two ANS archives: every defined field and every block's stream equal;
+    only the ORDER of the streams inside the data section (blockWords[k].y) may differ, since the
+    decoder addresses streams through those offsets.  Total size must match to the byte."""
+    a, b = parse_ans(mine), parse_ans(ref)
+    for k in ("magic", "num_blocks", "uncompressed", "total_words", "prob_bits", "use_checksum", "size"):
+        assert a[k] == b[k], f"{what}: field {k}: {a[k]} != {b[k]}"
+    if b["use_checksum"]:
+        assert a["checksum"] == b["checksum"], f"{what}: checksum"
+    assert np.array_equal(a["pdf"], b["pdf"]), f"{what}: pdf"
+    assert np.array_equal(a["states"], b["states"]), f"{what}: lane states"
+    assert np.array_equal(a["block_words"][:, 0], b["block_words"][:, 0]), f"{what}: block sizes"
+    # offsets: multiples of 8 words; the non-empty streams tile the data section exactly (an empty
+    # stream may sit at any offset inside it)
+    if a["num_blocks"]:
+        off = a["block_words"][:, 1].astype(np.int64)
+        ln = (((a["block_words"][:, 0] & 0xffff).astype(np.int64) + 7) // 8) * 8
+        assert np.all(off % 8 == 0), f"{what}: unaligned stream offset"
+        assert np.all(off + ln <= a["total_words"]), f"{what}: stream beyond the data section"
+        nz = ln > 0
+        o2, l2 = off[nz], ln[nz]
+        order = np.argsort(o2, kind="stable")
+        starts, ends = o2[order], o2[order] + l2[order]
+        if starts.size:
+            assert starts[0] == 0 and np.all(starts[1:] == ends[:-1]) and ends[-1] == a["total_words"], \
+                f"{what}: streams do not tile the data section"
+        else:
+            assert a["total_words"] == 0, f"{what}: total_words without streams"
+    for i, (x, y) in enumerate(zip(a["streams"], b["streams"])):
+        assert np.array_equal(x, y), f"{what}: stream of block {i}"
+
+
+def assert_same_float(mine, ref, ft: int, what: str = "") -> None:
+    """Float archives: header and stored planes byte-equal, ANS part semantically equal."""
+    m, r = _bytes(mine), _bytes(ref)
+    assert m.size == r.size, f"{what}: size {m.size} != {r.size}"
+    n = int(r[4:8].view(np.uint32)[0])
+    nc = float_noncomp_bytes(ft, n)
+    assert np.array_equal(m[:16 + nc], r[:16 + nc]), f"{what}: float header / stored planes"
+    assert_same_ans(m[16 + nc:], r[16 + nc:], what)

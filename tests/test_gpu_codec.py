@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI, via dietgpu_b200.ops) against the CPU oracle.
-Bit-exact everywhere: archives must equal the oracle's byte for byte (the encoder zeroes the bits
-the reference leaves undefined, as the oracle does), decode must reproduce the input."""
+Bit-exact everywhere: sizes, pdf, lane states, every block's stream and every decoded byte must equal
+the oracle's.  In the default encoder the ORDER of the streams inside an archive's data section is
+completion order (the format addresses streams by offset); with option encode_canonical=1 archives
+equal the oracle's byte for byte, which test_canonical_layout_is_byte_exact checks."""
 import numpy as np
 import pytest
 import torch
@@ -40,7 +42,7 @@ def ans_roundtrip(arrays, pb, checksum=False):
         got = comp[i, :hs[i]].cpu().numpy()
         assert hs[i] == want.size, f"member {i}: size {hs[i]} != oracle {want.size}"
         assert hs[i] % 16 == 0  # ans/ANSTest.cu:131-135
-        assert np.array_equal(got, want), f"member {i}: archive bytes differ from oracle"
+        O.assert_same_ans(got, want, f"member {i}")
         rows.append(comp[i, :hs[i]].clone())  # exactly-truncated buffers (ans_test.py:21-26)
     outs = [torch.empty_like(t) for t in ts]
     status = torch.zeros(len(ts), dtype=torch.uint8, device="cuda")
@@ -99,7 +101,8 @@ def test_ans_unaligned_inputs():
         comp, sizes, _ = dg().compress_data(False, [t])
         n = int(sizes[0])
         want = O.ans_encode(t.cpu().numpy(), 10)
-        assert n == want.size and np.array_equal(comp[0, :n].cpu().numpy(), want)
+        assert n == want.size
+        O.assert_same_ans(comp[0, :n].cpu().numpy(), want)
         out = torch.empty(20000 + 8, dtype=torch.uint8, device="cuda")[off % 8:][:20000]
         dg().decompress_data(False, [comp[0, :n]], [out])
         assert torch.equal(out, t)
@@ -154,7 +157,7 @@ def test_ans_split_size_api():
     splits = torch.tensor(sizes, dtype=torch.int32)
     rows, csz, _ = dg().compress_data_split_size(False, flat, splits, True)
     for i, a in enumerate(arrays):
-        assert np.array_equal(rows[i].cpu().numpy(), O.ans_encode(a, 10, True))
+        O.assert_same_ans(rows[i].cpu().numpy(), O.ans_encode(a, 10, True))
     out = torch.empty_like(flat)
     status = torch.zeros(len(sizes), dtype=torch.uint8, device="cuda")
     dg().decompress_data_split_size(False, rows, out, splits, True, None, status, None)
@@ -186,7 +189,7 @@ def test_ans_stride_api():
                                        comp.data_ptr(), ostride, csz.data_ptr(), st), "encode_stride")
     hs = csz.cpu().tolist()
     for i, a in enumerate(arrays):
-        assert np.array_equal(comp[i * ostride:i * ostride + hs[i]].cpu().numpy(), O.ans_encode(a, 10, True))
+        O.assert_same_ans(comp[i * ostride:i * ostride + hs[i]].cpu().numpy(), O.ans_encode(a, 10, True))
     out = torch.zeros(n * stride_in, dtype=torch.uint8, device="cuda")
     status = torch.zeros(n, dtype=torch.uint8, device="cuda")
     mism = (C.c_uint8 * n)()
@@ -211,7 +214,7 @@ def float_roundtrip(kind, word_arrays, pb=10, checksum=False, offsets=None):
     for i, w in enumerate(word_arrays):
         want = O.float_compress(ft, w, pb, checksum)
         assert hs[i] == want.size, f"member {i}: size {hs[i]} != oracle {want.size}"
-        assert np.array_equal(comp[i, :hs[i]].cpu().numpy(), want), f"member {i}: archive differs"
+        O.assert_same_float(comp[i, :hs[i]].cpu().numpy(), want, ft, f"member {i}")
         rows.append(comp[i, :hs[i]].clone())
     outs = []
     for i, t in enumerate(ts):
@@ -277,7 +280,7 @@ def test_float_split_size_api():
         rows, _, _ = dg().compress_data_split_size(True, flat, splits, True)
         ft = KINDS[kind][0]
         for r, a in zip(rows, arrs):
-            assert np.array_equal(r.cpu().numpy(), O.float_compress(ft, a, 10, True))
+            O.assert_same_float(r.cpu().numpy(), O.float_compress(ft, a, 10, True), ft)
         out = torch.empty_like(flat)
         dg().decompress_data_split_size(True, rows, out, splits, True)
         it = torch.int16 if kind != "f32" else torch.int32
@@ -306,7 +309,8 @@ def test_config2_zipf_256mib_roundtrip():
         hs = sizes.cpu().tolist()
         for i in (0, 1):
             want = O.ans_encode(members[i].cpu().numpy(), pb)
-            assert hs[i] == want.size and np.array_equal(comp[i, :hs[i]].cpu().numpy(), want)
+            assert hs[i] == want.size
+            O.assert_same_ans(comp[i, :hs[i]].cpu().numpy(), want)
         assert hs[:8] * 8 == hs
         outs = [torch.empty_like(t) for t in ts]
         dg().decompress_data(False, [comp[i, :hs[i]] for i in range(64)], outs, prob_bits=pb)
@@ -324,7 +328,8 @@ def test_config3_4_float_256mib_roundtrip(kind, batch, relu):
     comp, sizes, _ = dg().compress_data(True, ts)
     hs = sizes.cpu().tolist()
     want = O.float_compress(KINDS[kind][0], uniq[0], 10)
-    assert hs[0] == want.size and np.array_equal(comp[0, :hs[0]].cpu().numpy(), want)
+    assert hs[0] == want.size
+    O.assert_same_float(comp[0, :hs[0]].cpu().numpy(), want, KINDS[kind][0])
     outs = [torch.empty_like(t) for t in ts]
     dg().decompress_data(True, [comp[i, :hs[i]] for i in range(batch)], outs)
     for i in range(batch):
@@ -343,6 +348,35 @@ def test_single_member_256mib_bf16():
     assert torch.equal(out.view(torch.int16), w.view(torch.int16))
 
 
+def test_canonical_layout_is_byte_exact():
+    # option encode_canonical: streams packed in block order -> archives equal the oracle's byte for byte
+    from dietgpu_b200 import capi
+
+    capi.set_option("encode_canonical", 1)
+    try:
+        arrays = [zipf_bytes(300000, 1.1, 5), exp_bytes(4097, 50, 6), exp_bytes(70000, 10, 7), np.zeros(0, np.uint8)]
+        for pb in (9, 10, 11):
+            ts = [to_dev_bytes(a) for a in arrays]
+            comp, sizes, _ = dg().compress_data(False, ts, True, prob_bits=pb)
+            hs = sizes.cpu().tolist()
+            for i, a in enumerate(arrays):
+                assert np.array_equal(comp[i, :hs[i]].cpu().numpy(), O.ans_encode(a, pb, True))
+        for kind in ("bf16", "f16", "f32"):
+            ws = [normal_words(n, kind, n) for n in (100000, 4096, 33)]
+            ts = [words_to_tensor(w, kind) for w in ws]
+            comp, sizes, _ = dg().compress_data(True, ts, True)
+            hs = sizes.cpu().tolist()
+            for i, w in enumerate(ws):
+                assert np.array_equal(comp[i, :hs[i]].cpu().numpy(), O.float_compress(KINDS[kind][0], w, 10, True))
+            outs = [torch.empty_like(t) for t in ts]
+            dg().decompress_data(True, [comp[i, :hs[i]] for i in range(len(ts))], outs, True)
+            it = torch.int16 if kind != "f32" else torch.int32
+            for t, o in zip(ts, outs):
+                assert torch.equal(t.view(it), o.view(it))
+    finally:
+        capi.set_option("encode_canonical", 0)
+
+
 def test_kernel_variants_agree():
     # every tuning variant produces identical results
     from dietgpu_b200 import capi
@@ -350,13 +384,17 @@ def test_kernel_variants_agree():
     a = [zipf_bytes(300000, 1.1, 5), exp_bytes(4097, 50, 6)]
     try:
         for stage in (0, 1):
-            for dw in (2, 4, 8):
-                for ew in (2, 4, 8, 16):
-                    capi.set_option("decode_stage", stage)
-                    capi.set_option("decode_warps", dw)
-                    capi.set_option("encode_warps", ew)
-                    ans_roundtrip(a, 10)
+            for dw in (4, 8):
+                for ew in (2, 4, 8):
+                    for l64 in (0, 1):
+                        for canon in (0, 1):
+                            capi.set_option("decode_stage", stage)
+                            capi.set_option("decode_warps", dw)
+                            capi.set_option("encode_warps", ew)
+                            capi.set_option("decode_lut64", l64)
+                            capi.set_option("encode_canonical", canon)
+                            ans_roundtrip(a, 10)
     finally:
-        capi.set_option("decode_stage", 1)
-        capi.set_option("decode_warps", 4)
-        capi.set_option("encode_warps", 8)
+        for k, v in (("decode_stage", 1), ("decode_warps", 4), ("encode_warps", 8), ("decode_lut64", 0),
+                     ("encode_canonical", 0)):
+            capi.set_option(k, v)
