@@ -69,6 +69,7 @@ struct Options {
   int decode_lut64 = 0;      // 1: 8-byte decode LUT entries (fewer ALU ops, more smem)
   int decode_slot_words = 0; // TMA staging slot per warp in u16 words; 0 = auto
   int encode_warps = 8;      // warps per encode CTA (each warp is an independent worker)
+  int encode_slot_words = 0; // staging slot of the fast encoder in u16 words; 0 = auto
   int encode_canonical = 0;  // 1: streams packed in block order (byte-identical archives, slower)
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_mode = 0;         // 0: per-warp smem atomics; 1: per-lane private byte counters

@@ -33,6 +33,15 @@ namespace {
 
 constexpr int kStatsThreads = 256;  // == kNumSymbols: thread <-> symbol in the epilogue
 constexpr int kStatsWarps = kStatsThreads / 32;
+constexpr int kStatsUnroll = 4;     // independent 16 B loads in flight per thread
+
+__device__ __forceinline__ uint4 ldStream16(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
 
 struct EncodeScratch {
   MemberDesc* members;            // [n]
@@ -41,8 +50,8 @@ struct EncodeScratch {
   uint32_t* checksum;             // [n]           (zeroed)
   uint32_t* ticket;               // [4]           (zeroed)
   unsigned long long* lookback;   // [totalTickets](zeroed)   canonical (ordered) layout only
-  uint32_t* alloc;                // [n]           (zeroed)   words handed out so far per member
-  uint32_t* blocksDone;           // [n]           (zeroed)
+  unsigned long long* allocDone;  // [n]           (zeroed)   low: words handed out, high: blocks placed
+  uint8_t* spill;                 // [resident warps][maxBlockWords] u16: overflow of small staging slots
   EncEntry* table;                // [n][256]
   uint8_t* compRows;              // float kinds: [n] rows of compStride bytes
   uint32_t compStride;
@@ -224,17 +233,27 @@ statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, 
     const uint4* vec = reinterpret_cast<const uint4*>(in + head);
     for (uint32_t slab = blockIdx.y; slab < nSlabs; slab += gridDim.y) {
       const uint32_t v0 = slab * slabVecs, v1 = min(nVec, v0 + slabVecs);
-      for (uint32_t i = v0 + t; i < v1; i += kStatsThreads) {
-        const uint4 v = __ldg(vec + i);
-        xorAcc ^= v.x ^ v.y ^ v.z ^ v.w;
-        if (doHist) {
-          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      for (uint32_t i0 = v0 + t; i0 < v1; i0 += kStatsUnroll * kStatsThreads) {
+        uint4 vv[kStatsUnroll];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            atomicAdd(&wh[w4[k] & 0xffu], 1u);
-            atomicAdd(&wh[(w4[k] >> 8) & 0xffu], 1u);
-            atomicAdd(&wh[(w4[k] >> 16) & 0xffu], 1u);
-            atomicAdd(&wh[w4[k] >> 24], 1u);
+        for (int k = 0; k < kStatsUnroll; ++k) {
+          const uint32_t i = i0 + k * kStatsThreads;
+          vv[k] = i < v1 ? ldStream16(vec + i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < kStatsUnroll; ++k) {
+          if (i0 + k * kStatsThreads >= v1) break;
+          const uint4 v = vv[k];
+          xorAcc ^= v.x ^ v.y ^ v.z ^ v.w;
+          if (doHist) {
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              atomicAdd(&wh[w4[q] & 0xffu], 1u);
+              atomicAdd(&wh[(w4[q] >> 8) & 0xffu], 1u);
+              atomicAdd(&wh[(w4[q] >> 16) & 0xffu], 1u);
+              atomicAdd(&wh[w4[q] >> 24], 1u);
+            }
           }
         }
       }
@@ -307,44 +326,58 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs,
     const uint4* vec = reinterpret_cast<const uint4*>(in);
     for (uint32_t slab = blockIdx.y; slab < nSlabs; slab += gridDim.y) {
       const uint32_t v0 = slab * slabVecs, v1 = min(nVec, v0 + slabVecs);
-      for (uint32_t i = v0 + t; i < v1; i += kStatsThreads) {
-        const uint4 v = __ldg(vec + i);
-        if (FT == DGB_FLOAT32) {
-          const uint32_t r0 = __funnelshift_l(v.x, v.x, 1), r1 = __funnelshift_l(v.y, v.y, 1);
-          const uint32_t r2 = __funnelshift_l(v.z, v.z, 1), r3 = __funnelshift_l(v.w, v.w, 1);
-          // comp = top byte of each rotated word
-          const uint32_t c = __byte_perm(__byte_perm(r0, r1, 0x0073), __byte_perm(r2, r3, 0x0073), 0x5410);
-          reinterpret_cast<uint32_t*>(comp)[i] = c;
-          // u16 plane: low halves
-          uint2 lo;
-          lo.x = __byte_perm(r0, r1, 0x5410);
-          lo.y = __byte_perm(r2, r3, 0x5410);
-          reinterpret_cast<uint2*>(non)[i] = lo;
-          // u8 plane: byte 2 of each
-          const uint32_t hi = __byte_perm(__byte_perm(r0, r1, 0x0062), __byte_perm(r2, r3, 0x0062), 0x5410);
-          reinterpret_cast<uint32_t*>(non + 2u * roundUp(size, 8u))[i] = hi;
-          atomicAdd(&wh[c & 0xffu], 1u);
-          atomicAdd(&wh[(c >> 8) & 0xffu], 1u);
-          atomicAdd(&wh[(c >> 16) & 0xffu], 1u);
-          atomicAdd(&wh[c >> 24], 1u);
-        } else {
-          const uint32_t r0 = rot16x2<FT>(v.x), r1 = rot16x2<FT>(v.y);
-          const uint32_t r2 = rot16x2<FT>(v.z), r3 = rot16x2<FT>(v.w);
-          uint2 c, nn;
-          c.x = __byte_perm(r0, r1, 0x7531);
-          c.y = __byte_perm(r2, r3, 0x7531);
-          nn.x = __byte_perm(r0, r1, 0x6420);
-          nn.y = __byte_perm(r2, r3, 0x6420);
-          reinterpret_cast<uint2*>(comp)[i] = c;
-          reinterpret_cast<uint2*>(non)[i] = nn;
-          atomicAdd(&wh[c.x & 0xffu], 1u);
-          atomicAdd(&wh[(c.x >> 8) & 0xffu], 1u);
-          atomicAdd(&wh[(c.x >> 16) & 0xffu], 1u);
-          atomicAdd(&wh[c.x >> 24], 1u);
-          atomicAdd(&wh[c.y & 0xffu], 1u);
-          atomicAdd(&wh[(c.y >> 8) & 0xffu], 1u);
-          atomicAdd(&wh[(c.y >> 16) & 0xffu], 1u);
-          atomicAdd(&wh[c.y >> 24], 1u);
+      // four independent 16 B loads per thread are issued before any of them is consumed: the
+      // kernel is a pure stream and was latency-bound with one load in flight (ncu: 75 % of stall
+      // samples on the first use of the loaded vector, DRAM at 60 %)
+      for (uint32_t i0 = v0 + t; i0 < v1; i0 += kStatsUnroll * kStatsThreads) {
+        uint4 vv[kStatsUnroll];
+#pragma unroll
+        for (int k = 0; k < kStatsUnroll; ++k) {
+          const uint32_t i = i0 + k * kStatsThreads;
+          vv[k] = i < v1 ? ldStream16(vec + i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < kStatsUnroll; ++k) {
+          const uint32_t i = i0 + k * kStatsThreads;
+          if (i >= v1) break;
+          const uint4 v = vv[k];
+          if (FT == DGB_FLOAT32) {
+            const uint32_t r0 = __funnelshift_l(v.x, v.x, 1), r1 = __funnelshift_l(v.y, v.y, 1);
+            const uint32_t r2 = __funnelshift_l(v.z, v.z, 1), r3 = __funnelshift_l(v.w, v.w, 1);
+            // comp = top byte of each rotated word
+            const uint32_t c = __byte_perm(__byte_perm(r0, r1, 0x0073), __byte_perm(r2, r3, 0x0073), 0x5410);
+            reinterpret_cast<uint32_t*>(comp)[i] = c;
+            // u16 plane: low halves
+            uint2 lo;
+            lo.x = __byte_perm(r0, r1, 0x5410);
+            lo.y = __byte_perm(r2, r3, 0x5410);
+            reinterpret_cast<uint2*>(non)[i] = lo;
+            // u8 plane: byte 2 of each
+            const uint32_t hi = __byte_perm(__byte_perm(r0, r1, 0x0062), __byte_perm(r2, r3, 0x0062), 0x5410);
+            reinterpret_cast<uint32_t*>(non + 2u * roundUp(size, 8u))[i] = hi;
+            atomicAdd(&wh[c & 0xffu], 1u);
+            atomicAdd(&wh[(c >> 8) & 0xffu], 1u);
+            atomicAdd(&wh[(c >> 16) & 0xffu], 1u);
+            atomicAdd(&wh[c >> 24], 1u);
+          } else {
+            const uint32_t r0 = rot16x2<FT>(v.x), r1 = rot16x2<FT>(v.y);
+            const uint32_t r2 = rot16x2<FT>(v.z), r3 = rot16x2<FT>(v.w);
+            uint2 c, nn;
+            c.x = __byte_perm(r0, r1, 0x7531);
+            c.y = __byte_perm(r2, r3, 0x7531);
+            nn.x = __byte_perm(r0, r1, 0x6420);
+            nn.y = __byte_perm(r2, r3, 0x6420);
+            reinterpret_cast<uint2*>(comp)[i] = c;
+            reinterpret_cast<uint2*>(non)[i] = nn;
+            atomicAdd(&wh[c.x & 0xffu], 1u);
+            atomicAdd(&wh[(c.x >> 8) & 0xffu], 1u);
+            atomicAdd(&wh[(c.x >> 16) & 0xffu], 1u);
+            atomicAdd(&wh[c.x >> 24], 1u);
+            atomicAdd(&wh[c.y & 0xffu], 1u);
+            atomicAdd(&wh[(c.y >> 8) & 0xffu], 1u);
+            atomicAdd(&wh[(c.y >> 16) & 0xffu], 1u);
+            atomicAdd(&wh[c.y >> 24], 1u);
+          }
         }
       }
     }
@@ -537,10 +570,38 @@ __device__ __forceinline__ void encodeGroup(uint32_t& state, uint32_t ringLane, 
   }
 }
 
+// Staging slot smaller than the worst case: when it runs low, the words staged so far are moved
+// to this warp's global spill area (16 B granules; the < 8 leftover words slide to the slot start).
+struct Spill {
+  uint16_t* area;       // global, maxBlockWords(pb) words, 16 B aligned (nullptr: slot is worst-case sized)
+  uint32_t limitBytes;  // spill when more than this many bytes are staged
+  uint32_t spilled;     // words already in `area` (multiple of 8)
+};
+
+__device__ __forceinline__ void spillOut(Spill& sp, uint32_t stageAddr, uint16_t* stage, uint32_t& wa,
+                                         uint32_t lane) {
+  __syncwarp();
+  const uint32_t used = (wa - stageAddr) >> 1;
+  const uint32_t k = used & ~7u;
+  uint4* dst = reinterpret_cast<uint4*>(sp.area + sp.spilled);
+  const uint4* src = reinterpret_cast<const uint4*>(stage);
+  for (uint32_t i = lane; i < k / 8u; i += 32u) dst[i] = src[i];
+  const uint32_t left = used - k;
+  uint16_t v = 0;
+  if (lane < left) v = stage[k + lane];
+  __syncwarp();
+  if (lane < left) stage[lane] = v;
+  __syncwarp();
+  sp.spilled += k;
+  wa = stageAddr + 2u * left;
+}
+
 // Encodes bytes [0, n) of one block with one warp into the staging slot at
-// shared byte address `stageAddr`.  Returns the word count.
+// shared byte address `stageAddr` (spilling to sp.area when the slot is small).
+// Returns the TOTAL word count; the words not yet spilled are stage[0 .. total - sp.spilled).
 __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ in, uint32_t n,
                                                     uint32_t tabAddr, uint32_t stageAddr,
+                                                    uint16_t* stage, Spill& sp,
                                                     uint32_t ringAddr, uint32_t lane,
                                                     uint32_t& stateOut) {
   constexpr int U = kEncGroupRows;
@@ -549,6 +610,7 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
   const uint32_t ltMask = laneMaskLt();
   const uint32_t fullRows = n >> 5;
   uint32_t r = 0;
+  sp.spilled = 0;
   if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
     // input rows stream through the cp.async ring, two groups ahead of the encoder
     const uint32_t groups = fullRows / U;
@@ -561,22 +623,45 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
     for (uint32_t k = 0; k < groups; ++k) {
       if (k + 2 < groups) cpAsync16(dst + ((k + 2) & (kEncRingSlots - 1)) * (U * 32), src + (k + 2) * (U * 32));
       cpAsyncCommit();
+      if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
       cpAsyncWait<2>();
       __syncwarp();
       encodeGroup(state, ringAddr + (k & (kEncRingSlots - 1)) * (U * 32) + lane, tabAddr, wa, ltMask);
     }
     r = groups * U;
   }
+  // remaining rows (fewer than U, or all of them when the input is not 16 B aligned): every U rows
+  // the same spill check as above
   const uint8_t* p = in + lane + r * 32u;
-  for (; r < fullRows; ++r, p += 32) encodeStep(state, p[0], tabAddr, wa, ltMask);
+  for (uint32_t j = 0; r < fullRows; ++r, ++j, p += 32) {
+    if (sp.area && (j % U) == 0 && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
+    encodeStep(state, p[0], tabAddr, wa, ltMask);
+  }
   const uint32_t rem = n & 31u;
   if (rem) {
+    if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
     const bool valid = lane < rem;
     const uint32_t sym = valid ? p[0] : 0u;
     encodeStepPartial(valid, state, sym, tabAddr, wa, ltMask);
   }
   stateOut = state;
-  return (wa - stageAddr) >> 1;
+  return sp.spilled + ((wa - stageAddr) >> 1);
+}
+
+// Pads the block's stream to a multiple of 8 words and copies it to `dst` (global, 16 B aligned).
+__device__ __forceinline__ void placeStream(uint16_t* stage, Spill& sp, uint32_t words, uint32_t padded,
+                                            uint8_t* dst8, uint32_t lane) {
+  const uint32_t local = words - sp.spilled;        // words still in the slot
+  if (local + lane < padded - sp.spilled) stage[local + lane] = 0;  // pad < 8 words
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(dst8);
+  if (sp.spilled) {
+    const uint4* g = reinterpret_cast<const uint4*>(sp.area);
+    for (uint32_t i = lane; i < sp.spilled / 8u; i += 32u) dst[i] = __ldcg(g + i);
+    dst += sp.spilled / 8u;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(stage);
+  for (uint32_t i = lane; i < (padded - sp.spilled) / 8u; i += 32u) dst[i] = src[i];
 }
 
 constexpr unsigned long long kFlagAgg = 1ull << 32;
@@ -673,9 +758,9 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
     const uint32_t start = block * kBlockBytes;
     const uint32_t blockLen = min(kBlockBytes, size - start);
     uint32_t state;
-    const uint32_t words = encodeBlockWarp(ansIn + start, blockLen, tabAddr, stageAddr, ringAddr, lane, state);
+    Spill sp{nullptr, 0u, 0u};  // worst-case sized slot: never spills
+    const uint32_t words = encodeBlockWarp(ansIn + start, blockLen, tabAddr, stageAddr, myStage, sp, ringAddr, lane, state);
     const uint32_t padded = roundUp(words, 8u);
-    if (words + lane < padded) myStage[words + lane] = 0;  // pad < 8 words
 
     // ---- packed offset of this block: look-back over the member's earlier tickets ----
     uint32_t base = 0;
@@ -693,11 +778,7 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
     reinterpret_cast<uint32_t*>(pStates)[block * 32u + lane] = state;
     if (lane == 0)
       reinterpret_cast<uint2*>(pBlockWords)[block] = make_uint2((blockLen << 16) | words, base);
-    {
-      uint4* dst = reinterpret_cast<uint4*>(pData + 2u * (size_t)base);
-      const uint4* src = reinterpret_cast<const uint4*>(myStage);
-      for (uint32_t i = lane; i < padded / 8u; i += 32u) dst[i] = src[i];
-    }
+    placeStream(myStage, sp, words, padded, pData + 2u * (size_t)base, lane);
     if (block == nb - 1 && lane == 0) {
       // ans/GpuANSEncode.cuh:553-569 header (undefined bits zeroed)
       const uint32_t totalWords = base + padded;
@@ -729,12 +810,13 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
 // member by member (one shared table load per member) and its warps stride
 // over the blocks of the member.
 // ---------------------------------------------------------------------------
-__host__ __device__ constexpr uint32_t encFastWarpSmem(int pb) {
-  return kEncRingSlots * kEncGroupRows * 32u + maxBlockWords(pb) * 2u;  // ring + staging
+__host__ __device__ constexpr uint32_t encFastWarpSmem(uint32_t slotWords) {
+  return kEncRingSlots * kEncGroupRows * 32u + slotWords * 2u;  // ring + staging
 }
 
-__global__ void encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
-                                 uint32_t numMembers, uint32_t totalBlocks,
+__global__ void __launch_bounds__(256)
+encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
+                                 uint32_t numMembers, uint32_t totalBlocks, uint32_t slotWords,
                                  uint32_t* __restrict__ outSize) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(16) uint4 sTab[kNumSymbols];  // static: constant base for the hot LDS.128
@@ -742,8 +824,14 @@ __global__ void encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChe
   const uint32_t t = threadIdx.x, lane = t & 31u;
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
   const uint32_t W = blockDim.x >> 5;
-  uint8_t* mine = smem + (size_t)warp * encFastWarpSmem(pb);
+  uint8_t* mine = smem + (size_t)warp * encFastWarpSmem(slotWords);
   const uint32_t ringAddr = smemAddr(mine);
+  Spill sp;
+  sp.area = slotWords < maxBlockWords(pb)
+                ? reinterpret_cast<uint16_t*>(sc.spill) + (size_t)(blockIdx.x * W + warp) * maxBlockWords(pb)
+                : nullptr;
+  sp.limitBytes = (slotWords - kEncGroupRows * 32u - 8u) * 2u;  // a group emits at most 16*32 words
+  sp.spilled = 0;
   uint16_t* myStage = reinterpret_cast<uint16_t*>(mine + kEncRingSlots * kEncGroupRows * 32u);
   const uint32_t stageAddr = smemAddr(myStage);
   const uint32_t tabAddr = smemAddr(sTab);
@@ -795,35 +883,28 @@ __global__ void encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChe
       const uint32_t start = block * kBlockBytes;
       const uint32_t blockLen = min(kBlockBytes, size - start);
       uint32_t state;
-      const uint32_t words = encodeBlockWarp(ansIn + start, blockLen, tabAddr, stageAddr, ringAddr, lane, state);
+      const uint32_t words = encodeBlockWarp(ansIn + start, blockLen, tabAddr, stageAddr, myStage, sp, ringAddr, lane, state);
       const uint32_t padded = roundUp(words, 8u);
-      if (words + lane < padded) myStage[words + lane] = 0;  // pad < 8 words
-      // take a place in the data section
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(sc.alloc + m, padded);
+      // take a place in the data section: one 64-bit atomic hands out the word offset (low half)
+      // and counts finished blocks (high half), so no fence is needed to order the two
+      unsigned long long old = 0;
+      if (lane == 0) old = atomicAdd(sc.allocDone + m, (1ull << 32) | (unsigned long long)padded);
       reinterpret_cast<uint32_t*>(pStates)[block * 32u + lane] = state;
-      base = __shfl_sync(0xffffffffu, base, 0);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      const uint32_t base = (uint32_t)old;
       if (lane == 0)
         reinterpret_cast<uint2*>(pBlockWords)[block] = make_uint2((blockLen << 16) | words, base);
-      {
-        uint4* dst = reinterpret_cast<uint4*>(pData + 2u * (size_t)base);
-        const uint4* src = reinterpret_cast<const uint4*>(myStage);
-        for (uint32_t i = lane; i < padded / 8u; i += 32u) dst[i] = src[i];
-      }
-      // the block that completes the member writes the header
-      if (lane == 0) {
-        __threadfence();
-        if (atomicAdd(sc.blocksDone + m, 1u) == nb - 1u) {
-          __threadfence();
-          const uint32_t totalWords = atomicAdd(sc.alloc + m, 0u);
-          uint4* h = reinterpret_cast<uint4*>(ansOut);
-          h[0] = make_uint4(kAnsMagicVersion, nb, size, totalWords);
-          const bool ansChecksum = useChecksum && kind == kKindBytes;
-          h[1] = make_uint4((uint32_t)pb | ((ansChecksum ? 1u : 0u) << 4),
-                            ansChecksum ? __ldcg(sc.checksum + m) : 0u, 0u, 0u);
-          if (nb & 1u) reinterpret_cast<uint2*>(pBlockWords)[nb] = make_uint2(0u, 0u);
-          if (outSize) outSize[m] = ansOverhead(nb) + 2u * totalWords + extraBytes;
-        }
+      placeStream(myStage, sp, words, padded, pData + 2u * (size_t)base, lane);
+      // the block that takes the last place knows the member's total and writes the header
+      if (lane == 0 && (uint32_t)(old >> 32) == nb - 1u) {
+        const uint32_t totalWords = base + padded;
+        uint4* h = reinterpret_cast<uint4*>(ansOut);
+        h[0] = make_uint4(kAnsMagicVersion, nb, size, totalWords);
+        const bool ansChecksum = useChecksum && kind == kKindBytes;
+        h[1] = make_uint4((uint32_t)pb | ((ansChecksum ? 1u : 0u) << 4),
+                          ansChecksum ? __ldcg(sc.checksum + m) : 0u, 0u, 0u);
+        if (nb & 1u) reinterpret_cast<uint2*>(pBlockWords)[nb] = make_uint2(0u, 0u);
+        if (outSize) outSize[m] = ansOverhead(nb) + 2u * totalWords + extraBytes;
       }
       __syncwarp();  // staging and ring are reused by the next block
     }
@@ -834,8 +915,11 @@ __global__ void encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChe
 
 size_t alignUp256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// upper bound on resident encoder warps (64 per SM on up to 160 SMs): sizes the spill area
+constexpr uint32_t kMaxSpillWarps = 64u * 160u;
+
 struct ScratchPlan {
-  size_t members, zeroBegin, hist, histDone, checksum, ticket, alloc, blocksDone, lookback, zeroEnd, table, compRows, total;
+  size_t members, zeroBegin, hist, histDone, checksum, ticket, allocDone, lookback, zeroEnd, table, spill, compRows, total;
   uint32_t compStride;
 };
 
@@ -848,11 +932,11 @@ ScratchPlan planScratch(int kind, uint32_t n, uint32_t maxSize, uint32_t totalTi
   p.histDone = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
   p.checksum = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
   p.ticket = o; o = alignUp256(o + 16);
-  p.alloc = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
-  p.blocksDone = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
+  p.allocDone = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)n);
   p.lookback = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)totalTickets);
   p.zeroEnd = o;
   p.table = o; o = alignUp256(o + sizeof(EncEntry) * kNumSymbols * (size_t)n);
+  p.spill = o; o = alignUp256(o + (size_t)kMaxSpillWarps * maxBlockWords(11) * 2u);
   p.compStride = kind == kKindBytes ? 0u : roundUp(maxSize, 16u);
   p.compRows = o; o = alignUp256(o + (size_t)p.compStride * n);
   p.total = o;
@@ -888,7 +972,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   if (pb < 9 || pb > 11) return DGB_ERR_INVALID_ARG;
   if (kind != kKindBytes && histogram_dev) return DGB_ERR_INVALID_ARG;
   const Options& opt = options();
-  const uint32_t W = (uint32_t)std::max(1, std::min(opt.encode_warps, 16));  // warps per CTA
+  const uint32_t W = (uint32_t)std::max(1, std::min(opt.encode_warps, 8));  // warps per CTA
 
   std::vector<MemberDesc> desc(n);
   uint32_t maxSize = 0;
@@ -920,8 +1004,8 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   sc.checksum = reinterpret_cast<uint32_t*>(base + sp.checksum);
   sc.ticket = reinterpret_cast<uint32_t*>(base + sp.ticket);
   sc.lookback = reinterpret_cast<unsigned long long*>(base + sp.lookback);
-  sc.alloc = reinterpret_cast<uint32_t*>(base + sp.alloc);
-  sc.blocksDone = reinterpret_cast<uint32_t*>(base + sp.blocksDone);
+  sc.allocDone = reinterpret_cast<unsigned long long*>(base + sp.allocDone);
+  sc.spill = base + sp.spill;
   sc.table = reinterpret_cast<EncEntry*>(base + sp.table);
   sc.compRows = base + sp.compRows;
   sc.compStride = sp.compStride;
@@ -957,7 +1041,13 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   // ---- K2 ----
   if (totalTickets > 0) {
     const bool canonical = opt.encode_canonical != 0;
-    const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb) : encFastWarpSmem(pb));
+    // staging slot of the fast kernel: bytes compress little, float comp-bytes a lot; larger
+    // blocks spill to global scratch (correct for any input, just slower)
+    uint32_t slotWords = opt.encode_slot_words > 0 ? (uint32_t)opt.encode_slot_words
+                                                   : (kind == kKindBytes ? 2304u : 1536u);
+    slotWords = std::max<uint32_t>(roundUp(slotWords, 8u), kEncGroupRows * 32u + 264u);
+    slotWords = std::min(slotWords, maxBlockWords(pb));
+    const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb) : encFastWarpSmem(slotWords));
     static bool configured = false;
     if (!configured) {
       DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -992,7 +1082,8 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
       const uint64_t rounds = std::max<uint64_t>(1, (totalTickets + resident * W - 1) / (resident * W));
       const uint64_t want = ((uint64_t)totalTickets + W * rounds - 1) / (W * rounds);
       const uint32_t grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
-      encodeKernelFast<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, outSize_dev);
+      if ((uint64_t)grid2 * W > kMaxSpillWarps) return DGB_ERR_INVALID_ARG;
+      encodeKernelFast<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, slotWords, outSize_dev);
     }
     DGB_CUDA_TRY(cudaGetLastError());
     timerEnd(kSlotEncode, stream);

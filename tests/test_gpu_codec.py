@@ -377,6 +377,23 @@ def test_canonical_layout_is_byte_exact():
         capi.set_option("encode_canonical", 0)
 
 
+def test_small_staging_slot_spills():
+    # the fast encoder's staging slot can be smaller than a block's worst-case stream; force the
+    # spill path with the smallest slot on incompressible and on ragged inputs
+    from dietgpu_b200 import capi
+
+    capi.set_option("encode_slot_words", 776)
+    try:
+        arrays = [np.random.default_rng(5).integers(0, 256, 300000, dtype=np.uint8), zipf_bytes(123457, 1.0, 3),
+                  exp_bytes(4097, 2, 4), exp_bytes(31, 1, 5)]
+        for pb in (9, 10, 11):
+            ans_roundtrip(arrays, pb, checksum=True)
+        float_roundtrip("f32", [np.random.default_rng(6).integers(0, 2**32, 100000, dtype=np.uint32)], 10)
+        float_roundtrip("bf16", [np.random.default_rng(7).integers(0, 2**16, 200001, dtype=np.uint16)], 11)
+    finally:
+        capi.set_option("encode_slot_words", 0)
+
+
 def test_kernel_variants_agree():
     # every tuning variant produces identical results
     from dietgpu_b200 import capi
