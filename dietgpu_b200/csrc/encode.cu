@@ -814,7 +814,7 @@ __host__ __device__ constexpr uint32_t encFastWarpSmem(uint32_t slotWords) {
   return kEncRingSlots * kEncGroupRows * 32u + slotWords * 2u;  // ring + staging
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void
 encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
                                  uint32_t numMembers, uint32_t totalBlocks, uint32_t slotWords,
                                  uint32_t* __restrict__ outSize) {
