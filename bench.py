@@ -61,55 +61,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML in a thread DURING the timed region."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = str(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
 def make_batch(torch, kind, batch, per, seed, device):
@@ -131,37 +133,70 @@ def make_batch(torch, kind, batch, per, seed, device):
 
 
 class OursCodec:
+    """Device-resident codec calls through the C ABI (include/dietgpu_b200.h) with the host-side
+    pointer/size arrays prepared once, so the timed region measures the library, not Python list
+    handling.  `api_*` go through the public operator mirror (dietgpu_b200.ops) for the e2e leg."""
     name = "ours"
 
     def __init__(self, torch, kind, ts):
         import dietgpu_b200 as dg
         self.dg, self.torch, self.kind, self.ts = dg, torch, kind, ts
         self.as_float = kind != "bytes"
-        n = len(ts)
+        n = self.n = len(ts)
         dev = ts[0].device
         _, cols = (dg.max_float_compressed_output_size(ts) if self.as_float else dg.max_any_compressed_output_size(ts))
         self.comp = torch.empty((n, cols), dtype=torch.uint8, device=dev)
         self.sizes = torch.zeros(n, dtype=torch.int32, device=dev)
         self.outs = [torch.empty_like(t) for t in ts]
-        L = dg.capi.lib()
+        L = self.L = dg.capi.lib()
         mx = max(t.numel() for t in ts)
         if self.as_float:
-            ft = dg.ops._float_type(ts[0])
-            need = max(L.dgb_float_compress_temp_bytes(ft, n, mx), L.dgb_float_decompress_temp_bytes(ft, n, mx))
+            self.ft = dg.ops._float_type(ts[0])
+            need = max(L.dgb_float_compress_temp_bytes(self.ft, n, mx), L.dgb_float_decompress_temp_bytes(self.ft, n, mx))
         else:
             need = max(L.dgb_ans_encode_temp_bytes(n, mx), L.dgb_ans_decode_temp_bytes(n))
         self.temp = torch.empty(need + 512, dtype=torch.uint8, device=dev)
+        self.tp = self.temp.data_ptr() + (-self.temp.data_ptr()) % 256
+        self.tb = need
+        capi = dg.capi
+        self.in_ptrs = capi.ptr_array([t.data_ptr() for t in ts])
+        self.in_sizes = capi.u32_array([t.numel() if self.as_float else t.numel() * t.element_size() for t in ts])
+        self.row_ptrs = capi.ptr_array([self.comp.data_ptr() + i * cols for i in range(n)])
+        self.out_ptrs = capi.ptr_array([t.data_ptr() for t in self.outs])
         self.rows = None
 
+    def _stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
     def encode(self):
-        self.dg.compress_data(self.as_float, self.ts, False, self.temp, self.comp, self.sizes)
+        L = self.L
+        if self.as_float:
+            rc = L.dgb_float_compress_pointer(self.tp, self.tb, self.ft, 10, 0, self.n, self.in_ptrs, self.in_sizes,
+                                              self.row_ptrs, self.sizes.data_ptr(), self._stream())
+        else:
+            rc = L.dgb_ans_encode_pointer(self.tp, self.tb, 10, 0, self.n, self.in_ptrs, self.in_sizes, None,
+                                          self.row_ptrs, self.sizes.data_ptr(), self._stream())
+        assert rc == 0, rc
 
     def bind_rows(self):
         hs = self.sizes.cpu().tolist()
-        self.rows = [self.comp[i, :hs[i]] for i in range(len(self.ts))]
+        self.rows = [self.comp[i, :hs[i]] for i in range(self.n)]
         return hs
 
     def decode(self):
+        L = self.L
+        if self.as_float:
+            rc = L.dgb_float_decompress_pointer(self.tp, self.tb, self.ft, 10, 0, self.n, self.row_ptrs, self.out_ptrs,
+                                                self.in_sizes, None, None, None, self._stream())
+        else:
+            rc = L.dgb_ans_decode_pointer(self.tp, self.tb, 10, 0, self.n, self.row_ptrs, self.out_ptrs, self.in_sizes,
+                                          None, None, None, self._stream())
+        assert rc == 0, rc
+
+    def api_encode(self):
+        self.dg.compress_data(self.as_float, self.ts, False, self.temp, self.comp, self.sizes)
+
+    def api_decode(self):
         self.dg.decompress_data(self.as_float, self.rows, self.outs, False, self.temp)
 
     launches_per_step = 4  # stats + encode + plan + decode
@@ -187,11 +222,31 @@ class RefGpuCodec:
         self.codec = ref_lib.RefCodec(int(2.0 * total) + 256 * MIB, dev)  # no cudaMalloc fallback
         self.rows = None
 
+    def _prep(self):
+        from oracle import ref_lib
+        if getattr(self, "_ready", False):
+            return
+        self.RL = ref_lib.lib()
+        n = self.n = len(self.ts)
+        row = self.comp.size(1)
+        self.a_in = ref_lib._parr([t.data_ptr() for t in self.ts])
+        self.a_sz = ref_lib._uarr([t.numel() if self.as_float else t.numel() * t.element_size() for t in self.ts])
+        self.a_rows = ref_lib._parr([self.comp.data_ptr() + i * row for i in range(n)])
+        self.a_out = ref_lib._parr([t.data_ptr() for t in self.outs])
+        self.tptr, self.tbytes = self.codec.temp.data_ptr(), self.codec.temp.numel()
+        self._ready = True
+
+    def _stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
     def encode(self):
+        self._prep()
         if self.as_float:
-            self.codec.float_compress(self.ft, self.ts, self.comp, self.sizes)
+            self.RL.ref_float_compress(self.tptr, self.tbytes, self.ft, 10, 0, self.n, self.a_in, self.a_sz, self.a_rows,
+                                       self.sizes.data_ptr(), self._stream())
         else:
-            self.codec.ans_encode(self.ts, self.comp, self.sizes)
+            self.RL.ref_ans_encode_pointer(self.tptr, self.tbytes, 10, 0, self.n, self.a_in, self.a_sz, self.a_rows,
+                                           self.sizes.data_ptr(), self._stream())
 
     def bind_rows(self):
         hs = self.sizes.cpu().tolist()
@@ -199,10 +254,19 @@ class RefGpuCodec:
         return hs
 
     def decode(self):
+        self._prep()
         if self.as_float:
-            self.codec.float_decompress(self.ft, self.rows, self.outs)
+            self.RL.ref_float_decompress(self.tptr, self.tbytes, self.ft, 10, 0, 1, self.n, self.a_rows, self.a_out,
+                                         self.a_sz, None, None, self._stream())
         else:
-            self.codec.ans_decode(self.rows, self.outs)
+            self.RL.ref_ans_decode_pointer(self.tptr, self.tbytes, 10, 0, self.n, self.a_rows, self.a_out, self.a_sz,
+                                           None, None, self._stream())
+
+    def api_encode(self):
+        self.encode()
+
+    def api_decode(self):
+        self.decode()
 
     launches_per_step = 0
 
@@ -257,7 +321,7 @@ def cpu_baseline(kind, batch, per, budget_s=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
@@ -379,7 +443,7 @@ def main():
             nonlocal h2d, d2h
             for t, p in zip(ts, pin_in):          # host -> device: the step's inputs
                 t.copy_(p, non_blocking=True)
-            codec.encode()
+            codec.api_encode()
             hs2 = codec.sizes.cpu().tolist()      # device -> host: sizes, then the archives
             for i, n in enumerate(hs2):
                 pin_comp[i, :n].copy_(codec.comp[i, :n], non_blocking=True)
@@ -387,7 +451,7 @@ def main():
             for i, n in enumerate(hs2):           # host -> device: the archives
                 codec.comp[i, :n].copy_(pin_comp[i, :n], non_blocking=True)
             codec.rows = [codec.comp[i, :n] for i, n in enumerate(hs2)]
-            codec.decode()
+            codec.api_decode()
             for o, p in zip(codec.outs, pin_out):  # device -> host: the decoded floats
                 p.copy_(o, non_blocking=True)
             torch.cuda.synchronize()
