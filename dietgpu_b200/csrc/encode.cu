@@ -459,7 +459,10 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs,
 // There is no CTA-wide barrier anywhere in the loop (the first version's
 // per-ticket __syncthreads cost 27 % of all stall samples in ncu).
 // ---------------------------------------------------------------------------
-constexpr int kEncGroupRows = 16;      // rows per cp.async group: 32 lanes x 16 B = 512 B
+#ifndef DGB_ENC_GROUP_ROWS
+#define DGB_ENC_GROUP_ROWS 16
+#endif
+constexpr int kEncGroupRows = DGB_ENC_GROUP_ROWS;  // rows per cp.async group (16: all lanes copy 16 B; 8: lanes 0..15)
 constexpr uint32_t kEncRingSlots = 4;  // groups resident per warp
 
 __device__ __forceinline__ void cpAsync16(uint32_t dstSmem, const void* src) {
@@ -616,12 +619,14 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
     const uint32_t groups = fullRows / U;
     const uint8_t* src = in + lane * 16u;
     const uint32_t dst = ringAddr + lane * 16u;
-    if (groups > 0) cpAsync16(dst, src);
+    const bool copier = lane < (uint32_t)(U * 2);  // U*32 bytes per group, 16 B per copying lane
+    if (groups > 0 && copier) cpAsync16(dst, src);
     cpAsyncCommit();
-    if (groups > 1) cpAsync16(dst + U * 32, src + U * 32);
+    if (groups > 1 && copier) cpAsync16(dst + U * 32, src + U * 32);
     cpAsyncCommit();
     for (uint32_t k = 0; k < groups; ++k) {
-      if (k + 2 < groups) cpAsync16(dst + ((k + 2) & (kEncRingSlots - 1)) * (U * 32), src + (k + 2) * (U * 32));
+      if (k + 2 < groups && copier)
+        cpAsync16(dst + ((k + 2) & (kEncRingSlots - 1)) * (U * 32), src + (k + 2) * (U * 32));
       cpAsyncCommit();
       if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
       cpAsyncWait<2>();
