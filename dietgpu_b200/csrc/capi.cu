@@ -2,6 +2,7 @@
 // Maps the reference's three batch-addressing forms (pointer / stride / split
 // size; ans/BatchProvider.cuh) onto one internal member list, so every kernel
 // sees a single descriptor table uploaded in one copy.
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,6 +33,45 @@ cudaEvent_t takeEvent() {
 }
 thread_local TimedLaunch tlsOpen[kNumSlots];
 }  // namespace
+
+int streamPool(StreamPool** out) {
+  static StreamPool pool;
+  static bool ready = false;
+  if (!ready) {
+    for (int i = 0; i < kMaxParts; ++i) {
+      DGB_CUDA_TRY(cudaStreamCreateWithFlags(&pool.s[i], cudaStreamNonBlocking));
+      DGB_CUDA_TRY(cudaEventCreateWithFlags(&pool.done[i], cudaEventDisableTiming));
+    }
+    DGB_CUDA_TRY(cudaEventCreateWithFlags(&pool.start, cudaEventDisableTiming));
+    ready = true;
+  }
+  *out = &pool;
+  return DGB_OK;
+}
+
+void splitParts(const uint64_t* weight, uint32_t n, int parts, uint32_t* bounds) {
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n; ++i) total += weight[i];
+  bounds[0] = 0;
+  uint64_t acc = 0;
+  uint32_t idx = 0;
+  for (int p = 1; p < parts; ++p) {
+    const uint64_t target = total / (uint64_t)parts * (uint64_t)p;
+    const uint32_t mustLeave = (uint32_t)(parts - p);  // one member for every later part
+    while (idx + mustLeave < n && (idx < bounds[p - 1] + 1 || acc + weight[idx] / 2 <= target)) acc += weight[idx++];
+    bounds[p] = idx;
+  }
+  bounds[parts] = n;
+}
+
+int autoParts(int kind, uint32_t n, uint64_t totalBytes) {
+  const Options& o = options();
+  if (o.timing) return 1;  // per-kernel timing wants un-overlapped launches
+  int p = o.parts;
+  if (p <= 0) p = (kind != kKindBytes && n >= 8 && totalBytes >= (64ull << 20)) ? 2 : 1;
+  p = std::min(p, kMaxParts);
+  return (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)p, n));
+}
 
 void timerBegin(int slot, cudaStream_t stream) {
   if (!options().timing) return;
@@ -283,6 +323,7 @@ static int* optionSlot(const char* name) {
   if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
   if (!std::strcmp(name, "hist_mode")) return &o.hist_mode;
   if (!std::strcmp(name, "timing")) return &o.timing;
+  if (!std::strcmp(name, "parts")) return &o.parts;
   return nullptr;
 }
 

@@ -73,6 +73,7 @@ struct Options {
   int encode_canonical = 0;  // 1: streams packed in block order (byte-identical archives, slower)
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_mode = 0;         // 0: per-warp smem atomics; 1: per-lane private byte counters
+  int parts = 0;             // sub-batches run on internal streams (0 = auto, 1 = off, max 4)
   int timing = 0;            // 1: bracket every kernel launch with CUDA events (bench.py roofline pass)
 };
 Options& options();
@@ -101,6 +102,19 @@ void setLastCudaError(cudaError_t e);
 // Per-kernel timing (options().timing): slots are stable indices reported by
 // dgb_kernel_times().  No-ops when timing is off.
 enum TimerSlot : int { kSlotStats = 0, kSlotEncode = 1, kSlotPlan = 2, kSlotDecode = 3, kSlotChecksum = 4, kNumSlots = 5 };
+// Internal helper streams: a large batch is cut into up to kMaxParts contiguous sub-batches whose
+// kernels run on separate streams (forked from / joined to the caller's stream with events), so the
+// HBM-bound and the issue-bound kernels of different sub-batches overlap and launch gaps hide.
+constexpr int kMaxParts = 4;
+struct StreamPool {
+  cudaStream_t s[kMaxParts];
+  cudaEvent_t start, done[kMaxParts];
+};
+int streamPool(StreamPool** out);  // lazily created; DGB_OK or DGB_ERR_CUDA
+// cuts members [0,n) into `parts` contiguous ranges of roughly equal `weight`; bounds has parts+1 entries
+void splitParts(const uint64_t* weight, uint32_t n, int parts, uint32_t* bounds);
+int autoParts(int kind, uint32_t n, uint64_t totalBytes);
+
 void timerBegin(int slot, cudaStream_t stream);
 void timerEnd(int slot, cudaStream_t stream);
 

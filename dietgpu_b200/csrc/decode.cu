@@ -77,11 +77,13 @@ __device__ __forceinline__ ArchiveView openArchive(const uint8_t* in) {
 // ---------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(1024)
-planKernel(DecodeScratch sc, uint32_t n, int pb, uint8_t* __restrict__ outSuccess,
-           uint32_t* __restrict__ outSize, bool wantChecksum) {
+planKernel(DecodeScratch sc, uint32_t m0, uint32_t m1, uint32_t part, int pb,
+           uint8_t* __restrict__ outSuccess, uint32_t* __restrict__ outSize, bool wantChecksum) {
+  // members [m0, m1) form one sub-batch with its own flat block index space (totals[part])
   __shared__ uint32_t sWarp[32];
   uint32_t carry = 0;
-  for (uint32_t base = 0; base < n; base += blockDim.x) {
+  const uint32_t n = m1;
+  for (uint32_t base = m0; base < n; base += blockDim.x) {
     const uint32_t i = base + threadIdx.x;
     uint32_t blocks = 0;
     if (i < n) {
@@ -115,7 +117,7 @@ planKernel(DecodeScratch sc, uint32_t n, int pb, uint8_t* __restrict__ outSucces
     if (i < n) sc.members[i].work0 = carry + excl;
     carry += tot;
   }
-  if (threadIdx.x == 0) sc.totals[0] = carry;
+  if (threadIdx.x == 0) sc.totals[part] = carry;
 }
 
 // ---------------------------------------------------------------------------
@@ -479,7 +481,7 @@ __device__ void buildLut(const uint8_t* __restrict__ ans, typename Lut<PB, LUT64
 
 template <int KIND, int PB, int WARPS, bool STAGE, bool LUT64>
 __global__ void __launch_bounds__(WARPS * 32, DGB_DECODE_WARPS_PER_SM / WARPS)
-decodeKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords) {
+decodeKernel(DecodeScratch sc, uint32_t m0, uint32_t m1, uint32_t part, uint32_t slotWords) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t K = 1u << PB;
   typedef typename Lut<PB, LUT64>::Entry Entry;
@@ -507,7 +509,7 @@ decodeKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords) {
     __syncthreads();
   }
 
-  const uint32_t total = __ldcg(sc.totals);
+  const uint32_t total = __ldcg(sc.totals + part);
   // contiguous, balanced run of flat blocks for this CTA
   const uint64_t g = gridDim.x;
   uint32_t cur = (uint32_t)((uint64_t)total * blockIdx.x / g);
@@ -517,7 +519,7 @@ decodeKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords) {
     // member containing flat block `cur`: the last member whose first block <= cur (members
     // that contribute no blocks share their successor's start and are skipped by the search)
     if (t == 0) {
-      uint32_t lo = 0, hi = n;
+      uint32_t lo = m0, hi = m1;
       while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (__ldcg(&sc.members[mid].work0) <= cur) lo = mid; else hi = mid;
@@ -598,7 +600,7 @@ DecodePlan planDecodeScratch(uint32_t n) {
   DecodePlan p{};
   size_t o = 0;
   p.members = o; o = alignUp256(o + sizeof(MemberDesc) * (size_t)n);
-  p.totals = o; o = alignUp256(o + 16);
+  p.totals = o; o = alignUp256(o + 4 * kMaxParts);
   p.checksum = o; o = alignUp256(o + 4 * (size_t)n);
   p.archiveChecksum = o; o = alignUp256(o + 4 * (size_t)n);
   p.sizes = o; o = alignUp256(o + 4 * (size_t)n);
@@ -618,7 +620,8 @@ int smCountD() {
 }
 
 template <int KIND, int PB, int WARPS, bool STAGE, bool LUT64>
-int launchDecode(const DecodeScratch& sc, uint32_t n, uint64_t blockBound, cudaStream_t stream) {
+int launchDecode(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t part, uint64_t blockBound,
+                 cudaStream_t stream) {
   auto kern = decodeKernel<KIND, PB, WARPS, STAGE, LUT64>;
   const Options& opt = options();
   // staging slot per warp: worst case for raw bytes; float kinds code exponent-like bytes that
@@ -649,43 +652,45 @@ int launchDecode(const DecodeScratch& sc, uint32_t n, uint64_t blockBound, cudaS
   const uint64_t want = (blockBound + WARPS * rounds - 1) / (WARPS * rounds);
   const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
   timerBegin(kSlotDecode, stream);
-  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, n, slotWords);
+  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, m0, m1, part, slotWords);
   DGB_CUDA_TRY(cudaGetLastError());
   timerEnd(kSlotDecode, stream);
   return DGB_OK;
 }
 
 template <int KIND, int PB, int WARPS>
-int launchDecodeV(const DecodeScratch& sc, uint32_t n, uint64_t blockBound, cudaStream_t stream) {
+int launchDecodeV(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t part, uint64_t blockBound,
+                  cudaStream_t stream) {
   const Options& opt = options();
   const bool stage = opt.decode_stage != 0, l64 = opt.decode_lut64 != 0;
   if (stage) {
-    return l64 ? launchDecode<KIND, PB, WARPS, true, true>(sc, n, blockBound, stream)
-               : launchDecode<KIND, PB, WARPS, true, false>(sc, n, blockBound, stream);
+    return l64 ? launchDecode<KIND, PB, WARPS, true, true>(sc, m0, m1, part, blockBound, stream)
+               : launchDecode<KIND, PB, WARPS, true, false>(sc, m0, m1, part, blockBound, stream);
   }
-  return l64 ? launchDecode<KIND, PB, WARPS, false, true>(sc, n, blockBound, stream)
-             : launchDecode<KIND, PB, WARPS, false, false>(sc, n, blockBound, stream);
+  return l64 ? launchDecode<KIND, PB, WARPS, false, true>(sc, m0, m1, part, blockBound, stream)
+             : launchDecode<KIND, PB, WARPS, false, false>(sc, m0, m1, part, blockBound, stream);
 }
 
 template <int KIND, int PB>
-int launchDecodeW(const DecodeScratch& sc, uint32_t n, uint64_t blockBound, cudaStream_t stream) {
+int launchDecodeW(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t part, uint64_t blockBound,
+                  cudaStream_t stream) {
   switch (options().decode_warps) {
-    case 8: return launchDecodeV<KIND, PB, 8>(sc, n, blockBound, stream);
-    default: return launchDecodeV<KIND, PB, 4>(sc, n, blockBound, stream);
+    case 8: return launchDecodeV<KIND, PB, 8>(sc, m0, m1, part, blockBound, stream);
+    default: return launchDecodeV<KIND, PB, 4>(sc, m0, m1, part, blockBound, stream);
   }
 }
 
 template <int KIND>
-int decodeKind(const DecodeScratch& sc, int pb, bool checksum, uint32_t n, uint64_t blockBound,
-               uint8_t* outSuccess, uint32_t* outSize, cudaStream_t stream) {
+int decodeKind(const DecodeScratch& sc, int pb, bool checksum, uint32_t m0, uint32_t m1, uint32_t part,
+               uint64_t blockBound, uint8_t* outSuccess, uint32_t* outSize, cudaStream_t stream) {
   timerBegin(kSlotPlan, stream);
-  planKernel<KIND><<<1, 1024, 0, stream>>>(sc, n, pb, outSuccess, outSize, checksum);
+  planKernel<KIND><<<1, 1024, 0, stream>>>(sc, m0, m1, part, pb, outSuccess, outSize, checksum);
   DGB_CUDA_TRY(cudaGetLastError());
   timerEnd(kSlotPlan, stream);
   switch (pb) {
-    case 9: return launchDecodeW<KIND, 9>(sc, n, blockBound, stream);
-    case 10: return launchDecodeW<KIND, 10>(sc, n, blockBound, stream);
-    case 11: return launchDecodeW<KIND, 11>(sc, n, blockBound, stream);
+    case 9: return launchDecodeW<KIND, 9>(sc, m0, m1, part, blockBound, stream);
+    case 10: return launchDecodeW<KIND, 10>(sc, m0, m1, part, blockBound, stream);
+    case 11: return launchDecodeW<KIND, 11>(sc, m0, m1, part, blockBound, stream);
     default: return DGB_ERR_INVALID_ARG;
   }
 }
@@ -704,7 +709,6 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   if (reinterpret_cast<uintptr_t>(temp) & 255u) return DGB_ERR_INVALID_ARG;
 
   std::vector<MemberDesc> desc(n);
-  uint64_t blockBound = 0;
   const uint32_t wordBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
   for (uint32_t i = 0; i < n; ++i) {
     if (!members[i].in || (members[i].size && !members[i].out)) return DGB_ERR_INVALID_ARG;
@@ -715,7 +719,6 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     desc[i].out = members[i].out;
     desc[i].size = members[i].size;  // capacity
     desc[i].work0 = 0;
-    blockBound += divUp(members[i].size, kBlockBytes);
   }
   uint8_t* base = static_cast<uint8_t*>(temp);
   DecodeScratch sc;
@@ -728,15 +731,44 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
                                cudaMemcpyHostToDevice, stream));
   if (checksum) DGB_CUDA_TRY(cudaMemsetAsync(sc.checksum, 0, 4 * (size_t)n, stream));
 
-  int rc;
-  switch (kind) {
-    case kKindBytes: rc = decodeKind<kKindBytes>(sc, pb, checksum, n, blockBound, outSuccess_dev, outSize_dev, stream); break;
-    case kKindF16: rc = decodeKind<kKindF16>(sc, pb, checksum, n, blockBound, outSuccess_dev, outSize_dev, stream); break;
-    case kKindBF16: rc = decodeKind<kKindBF16>(sc, pb, checksum, n, blockBound, outSuccess_dev, outSize_dev, stream); break;
-    case kKindF32: rc = decodeKind<kKindF32>(sc, pb, checksum, n, blockBound, outSuccess_dev, outSize_dev, stream); break;
-    default: return DGB_ERR_INVALID_ARG;
+  // sub-batches on internal streams: the plan kernel (pure latency) of one part hides behind the
+  // decode kernel of another, and the tail of one decode kernel overlaps the next
+  std::vector<uint64_t> weight(n);
+  uint64_t totalBytes = 0;
+  for (uint32_t i = 0; i < n; ++i) { weight[i] = (uint64_t)desc[i].size * wordBytes; totalBytes += weight[i]; }
+  const int parts = autoParts(kind, n, totalBytes);
+  uint32_t bounds[kMaxParts + 1];
+  splitParts(weight.data(), n, parts, bounds);
+  StreamPool* pool = nullptr;
+  if (parts > 1) {
+    int prc = streamPool(&pool);
+    if (prc != DGB_OK) return prc;
+    DGB_CUDA_TRY(cudaEventRecord(pool->start, stream));
   }
-  if (rc != DGB_OK) return rc;
+  for (int part = 0; part < parts; ++part) {
+    const uint32_t m0 = bounds[part], m1 = bounds[part + 1];
+    if (m1 == m0) continue;
+    cudaStream_t ps = stream;
+    if (parts > 1) {
+      ps = pool->s[part];
+      DGB_CUDA_TRY(cudaStreamWaitEvent(ps, pool->start, 0));
+    }
+    uint64_t partBound = 0;
+    for (uint32_t i = m0; i < m1; ++i) partBound += divUp(desc[i].size, kBlockBytes);
+    int rc;
+    switch (kind) {
+      case kKindBytes: rc = decodeKind<kKindBytes>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+      case kKindF16: rc = decodeKind<kKindF16>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+      case kKindBF16: rc = decodeKind<kKindBF16>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+      case kKindF32: rc = decodeKind<kKindF32>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+      default: return DGB_ERR_INVALID_ARG;
+    }
+    if (rc != DGB_OK) return rc;
+    if (parts > 1) {
+      DGB_CUDA_TRY(cudaEventRecord(pool->done[part], ps));
+      DGB_CUDA_TRY(cudaStreamWaitEvent(stream, pool->done[part], 0));
+    }
+  }
 
   if (checksum) {
     // ans/GpuANSDecode.cuh:555-591 / float/GpuFloatDecompress.cuh:698-733: checksum the

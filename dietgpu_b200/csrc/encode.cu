@@ -199,9 +199,9 @@ __device__ bool flushAndTicket(uint32_t (*sHist)[kNumSymbols], uint32_t* histGlo
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kStatsThreads)
 statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, int pb,
-                 bool useChecksum, uint32_t slabVecs, uint32_t* __restrict__ outSize) {
+                 bool useChecksum, uint32_t slabVecs, uint32_t memberBase, uint32_t* __restrict__ outSize) {
   __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
-  const uint32_t m = blockIdx.x, t = threadIdx.x, warp = t >> 5;
+  const uint32_t m = blockIdx.x + memberBase, t = threadIdx.x, warp = t >> 5;
   const MemberDesc md = sc.members[m];
   const uint8_t* in = static_cast<const uint8_t*>(md.in);
   const uint32_t size = md.size;
@@ -292,12 +292,12 @@ __device__ __forceinline__ uint32_t rot16x2(uint32_t w) {
 
 template <int FT>
 __global__ void __launch_bounds__(kStatsThreads)
-statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs,
+statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, uint32_t memberBase,
                  uint32_t* __restrict__ outSize) {
   __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
   constexpr uint32_t EPV = (FT == DGB_FLOAT32) ? 4u : 8u;  // elements per 16 B vector
   constexpr uint32_t WB = (FT == DGB_FLOAT32) ? 4u : 2u;   // word bytes
-  const uint32_t m = blockIdx.x, t = threadIdx.x, warp = t >> 5;
+  const uint32_t m = blockIdx.x + memberBase, t = threadIdx.x, warp = t >> 5;
   const MemberDesc md = sc.members[m];
   const uint8_t* in = static_cast<const uint8_t*>(md.in);
   const uint32_t size = md.size;  // float words
@@ -821,7 +821,8 @@ __host__ __device__ constexpr uint32_t encFastWarpSmem(uint32_t slotWords) {
 
 __global__ void
 encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
-                                 uint32_t numMembers, uint32_t totalBlocks, uint32_t slotWords,
+                                 uint32_t numMembers, uint32_t blockBegin, uint32_t blockEnd,
+                                 uint32_t slotWords, uint32_t spillWarpBase,
                                  uint32_t* __restrict__ outSize) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(16) uint4 sTab[kNumSymbols];  // static: constant base for the hot LDS.128
@@ -833,7 +834,7 @@ encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
   const uint32_t ringAddr = smemAddr(mine);
   Spill sp;
   sp.area = slotWords < maxBlockWords(pb)
-                ? reinterpret_cast<uint16_t*>(sc.spill) + (size_t)(blockIdx.x * W + warp) * maxBlockWords(pb)
+                ? reinterpret_cast<uint16_t*>(sc.spill) + (size_t)(spillWarpBase + blockIdx.x * W + warp) * maxBlockWords(pb)
                 : nullptr;
   sp.limitBytes = (slotWords - kEncGroupRows * 32u - 8u) * 2u;  // a group emits at most 16*32 words
   sp.spilled = 0;
@@ -841,9 +842,9 @@ encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
   const uint32_t stageAddr = smemAddr(myStage);
   const uint32_t tabAddr = smemAddr(sTab);
 
-  const uint64_t g = gridDim.x;
-  uint32_t cur = (uint32_t)((uint64_t)totalBlocks * blockIdx.x / g);
-  const uint32_t end = (uint32_t)((uint64_t)totalBlocks * (blockIdx.x + 1) / g);
+  const uint64_t g = gridDim.x, span = blockEnd - blockBegin;
+  uint32_t cur = blockBegin + (uint32_t)(span * blockIdx.x / g);
+  const uint32_t end = blockBegin + (uint32_t)(span * (blockIdx.x + 1) / g);
 
   while (cur < end) {
     if (t == 0) {
@@ -1019,79 +1020,112 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
                                cudaMemcpyHostToDevice, stream));
   DGB_CUDA_TRY(cudaMemsetAsync(base + sp.zeroBegin, 0, sp.zeroEnd - sp.zeroBegin, stream));
 
-  // ---- K1 ----
   const int sms = smCount();
   const uint32_t elemBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
-  const uint32_t slabVecs = std::max(1, opt.hist_slab_kb) * 1024u / 16u;
-  const uint64_t maxVecs = ((uint64_t)maxSize * elemBytes) / 16u;
-  uint32_t gridY = (uint32_t)std::max<uint64_t>(1, (maxVecs + slabVecs - 1) / slabVecs);
-  // enough CTAs to fill the machine a few times, never more than the slabs
-  const uint32_t wantY = std::max(1u, (uint32_t)(8 * sms * 4) / n);
-  gridY = std::min(std::min(gridY, wantY), 65535u);
-  dim3 grid1(n, gridY);
-  timerBegin(kSlotStats, stream);
-  if (kind == kKindBytes) {
-    statsBytesKernel<<<grid1, kStatsThreads, 0, stream>>>(sc, histogram_dev, pb, checksum, slabVecs,
-                                                          outSize_dev);
-  } else if (kind == kKindF16) {
-    statsFloatKernel<DGB_FLOAT16><<<grid1, kStatsThreads, 0, stream>>>(sc, pb, checksum, slabVecs, outSize_dev);
-  } else if (kind == kKindBF16) {
-    statsFloatKernel<DGB_BFLOAT16><<<grid1, kStatsThreads, 0, stream>>>(sc, pb, checksum, slabVecs, outSize_dev);
-  } else {
-    statsFloatKernel<DGB_FLOAT32><<<grid1, kStatsThreads, 0, stream>>>(sc, pb, checksum, slabVecs, outSize_dev);
-  }
-  DGB_CUDA_TRY(cudaGetLastError());
-  timerEnd(kSlotStats, stream);
+  const bool canonical = opt.encode_canonical != 0;
 
-  // ---- K2 ----
-  if (totalTickets > 0) {
-    const bool canonical = opt.encode_canonical != 0;
-    // staging slot of the fast kernel: bytes compress little, float comp-bytes a lot; larger
-    // blocks spill to global scratch (correct for any input, just slower)
-    uint32_t slotWords = opt.encode_slot_words > 0 ? (uint32_t)opt.encode_slot_words
-                                                   : (kind == kKindBytes ? 2304u : 1536u);
-    slotWords = std::max<uint32_t>(roundUp(slotWords, 8u), kEncGroupRows * 32u + 264u);
-    slotWords = std::min(slotWords, maxBlockWords(pb));
-    const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb) : encFastWarpSmem(slotWords));
-    static bool configured = false;
-    if (!configured) {
-      DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(200 * 1024)));
-      DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(200 * 1024)));
-      configured = true;
-    }
-    static size_t occKeySmem = 0;
-    static uint32_t occKeyW = 0;
-    static int occKeyCanon = -1;
-    static int perSm = 1;
-    if (occKeySmem != smemBytes || occKeyW != W || occKeyCanon != (int)canonical) {
-      int occ = 0;
-      if (canonical) {
-        DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel, (int)(W * 32), smemBytes));
-      } else {
-        DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast, (int)(W * 32), smemBytes));
-      }
-      perSm = std::max(occ, 1);
-      occKeySmem = smemBytes;
-      occKeyW = W;
-      occKeyCanon = (int)canonical;
-    }
-    timerBegin(kSlotEncode, stream);
+  // ---- sub-batches on internal streams (the ordered canonical encoder stays on one stream) ----
+  std::vector<uint64_t> weight(n);
+  uint64_t totalBytes = 0;
+  for (uint32_t i = 0; i < n; ++i) { weight[i] = (uint64_t)desc[i].size * elemBytes; totalBytes += weight[i]; }
+  // byte inputs measured slightly slower when split (their stats kernel is atomics-bound, not HBM-bound)
+  const int parts = canonical ? 1 : autoParts(kind, n, totalBytes);
+  uint32_t bounds[kMaxParts + 1];
+  splitParts(weight.data(), n, parts, bounds);
+  StreamPool* pool = nullptr;
+  if (parts > 1) {
+    int rc = streamPool(&pool);
+    if (rc != DGB_OK) return rc;
+    DGB_CUDA_TRY(cudaEventRecord(pool->start, stream));
+  }
+
+  // K2 launch configuration (same for every part)
+  uint32_t slotWords = opt.encode_slot_words > 0 ? (uint32_t)opt.encode_slot_words
+                                                 : (kind == kKindBytes ? 2304u : 1536u);
+  slotWords = std::max<uint32_t>(roundUp(slotWords, 8u), kEncGroupRows * 32u + 264u);
+  slotWords = std::min(slotWords, maxBlockWords(pb));
+  const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb) : encFastWarpSmem(slotWords));
+  static bool configured = false;
+  if (!configured) {
+    DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    configured = true;
+  }
+  static size_t occKeySmem = 0;
+  static uint32_t occKeyW = 0;
+  static int occKeyCanon = -1;
+  static int perSm = 1;
+  if (occKeySmem != smemBytes || occKeyW != W || occKeyCanon != (int)canonical) {
+    int occ = 0;
     if (canonical) {
-      const uint32_t grid2 = std::min<uint32_t>(divUp(totalTickets, W), (uint32_t)(perSm * sms));
-      encodeKernel<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, outSize_dev);
+      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel, (int)(W * 32), smemBytes));
     } else {
-      // one resident wave, equal rounds per warp (see launchDecode)
-      const uint64_t resident = (uint64_t)perSm * sms;
-      const uint64_t rounds = std::max<uint64_t>(1, (totalTickets + resident * W - 1) / (resident * W));
-      const uint64_t want = ((uint64_t)totalTickets + W * rounds - 1) / (W * rounds);
-      const uint32_t grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
-      if ((uint64_t)grid2 * W > kMaxSpillWarps) return DGB_ERR_INVALID_ARG;
-      encodeKernelFast<<<grid2, W * 32, smemBytes, stream>>>(sc, kind, pb, checksum, n, totalTickets, slotWords, outSize_dev);
+      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast, (int)(W * 32), smemBytes));
+    }
+    perSm = std::max(occ, 1);
+    occKeySmem = smemBytes;
+    occKeyW = W;
+    occKeyCanon = (int)canonical;
+  }
+  const uint64_t resident = (uint64_t)perSm * sms;
+  const uint32_t spillWarpsPerPart = kMaxSpillWarps / (uint32_t)parts;
+
+  for (int part = 0; part < parts; ++part) {
+    const uint32_t m0 = bounds[part], m1 = bounds[part + 1];
+    if (m1 == m0) continue;
+    cudaStream_t ps = stream;
+    if (parts > 1) {
+      ps = pool->s[part];
+      DGB_CUDA_TRY(cudaStreamWaitEvent(ps, pool->start, 0));
+    }
+    // ---- K1 ----
+    uint32_t partMax = 0;
+    for (uint32_t i = m0; i < m1; ++i) partMax = std::max(partMax, desc[i].size);
+    const uint32_t slabVecs = std::max(1, opt.hist_slab_kb) * 1024u / 16u;
+    const uint64_t maxVecs = ((uint64_t)partMax * elemBytes) / 16u;
+    uint32_t gridY = (uint32_t)std::max<uint64_t>(1, (maxVecs + slabVecs - 1) / slabVecs);
+    // enough CTAs to fill the machine a few times, never more than the slabs
+    const uint32_t wantY = std::max(1u, (uint32_t)(8 * sms * 4) / (m1 - m0));
+    gridY = std::min(std::min(gridY, wantY), 65535u);
+    dim3 grid1(m1 - m0, gridY);
+    timerBegin(kSlotStats, ps);
+    if (kind == kKindBytes) {
+      statsBytesKernel<<<grid1, kStatsThreads, 0, ps>>>(sc, histogram_dev, pb, checksum, slabVecs, m0, outSize_dev);
+    } else if (kind == kKindF16) {
+      statsFloatKernel<DGB_FLOAT16><<<grid1, kStatsThreads, 0, ps>>>(sc, pb, checksum, slabVecs, m0, outSize_dev);
+    } else if (kind == kKindBF16) {
+      statsFloatKernel<DGB_BFLOAT16><<<grid1, kStatsThreads, 0, ps>>>(sc, pb, checksum, slabVecs, m0, outSize_dev);
+    } else {
+      statsFloatKernel<DGB_FLOAT32><<<grid1, kStatsThreads, 0, ps>>>(sc, pb, checksum, slabVecs, m0, outSize_dev);
     }
     DGB_CUDA_TRY(cudaGetLastError());
-    timerEnd(kSlotEncode, stream);
+    timerEnd(kSlotStats, ps);
+
+    // ---- K2 ----
+    const uint32_t blockBegin = desc[m0].work0;
+    const uint32_t blockEnd = m1 < n ? desc[m1].work0 : totalTickets;
+    const uint32_t partBlocks = blockEnd - blockBegin;
+    if (partBlocks > 0) {
+      timerBegin(kSlotEncode, ps);
+      if (canonical) {
+        const uint32_t grid2 = std::min<uint32_t>(divUp(totalTickets, W), (uint32_t)resident);
+        encodeKernel<<<grid2, W * 32, smemBytes, ps>>>(sc, kind, pb, checksum, n, totalTickets, outSize_dev);
+      } else {
+        // one resident wave, equal rounds per warp (see launchDecode)
+        const uint64_t rounds = std::max<uint64_t>(1, (partBlocks + resident * W - 1) / (resident * W));
+        const uint64_t want = ((uint64_t)partBlocks + W * rounds - 1) / (W * rounds);
+        uint32_t grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
+        grid2 = std::max(1u, std::min(grid2, spillWarpsPerPart / W));  // every warp owns a spill slot
+        encodeKernelFast<<<grid2, W * 32, smemBytes, ps>>>(sc, kind, pb, checksum, n, blockBegin, blockEnd, slotWords,
+                                                         (uint32_t)part * spillWarpsPerPart, outSize_dev);
+      }
+      DGB_CUDA_TRY(cudaGetLastError());
+      timerEnd(kSlotEncode, ps);
+    }
+    if (parts > 1) {
+      DGB_CUDA_TRY(cudaEventRecord(pool->done[part], ps));
+      DGB_CUDA_TRY(cudaStreamWaitEvent(stream, pool->done[part], 0));
+    }
   }
   return DGB_OK;
 }

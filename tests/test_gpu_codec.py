@@ -394,6 +394,23 @@ def test_small_staging_slot_spills():
         capi.set_option("encode_slot_words", 0)
 
 
+def test_sub_batch_streams():
+    # large batches are cut into sub-batches that run on internal streams; force 1/2/4 parts on
+    # batches of 1, 3 and many members (incl. empty members) and check parity each time
+    from dietgpu_b200 import capi
+
+    try:
+        for parts in (1, 2, 4):
+            capi.set_option("parts", parts)
+            ans_roundtrip([zipf_bytes(50000, 1.0, 1)], 10)
+            ans_roundtrip([exp_bytes(9000, 5, 2), np.zeros(0, np.uint8), exp_bytes(70000, 50, 3)], 10, checksum=True)
+            ans_roundtrip([exp_bytes(1000 + 513 * i, 20, i) for i in range(37)], 11)
+            float_roundtrip("bf16", [normal_words(3000 + 1111 * i, "bf16", i) for i in range(19)], 10, checksum=True)
+            float_roundtrip("f32", [normal_words(5000, "f32", 1), normal_words(0, "f32", 2)], 10)
+    finally:
+        capi.set_option("parts", 0)
+
+
 def test_kernel_variants_agree():
     # every tuning variant produces identical results
     from dietgpu_b200 import capi
