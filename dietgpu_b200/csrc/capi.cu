@@ -322,6 +322,7 @@ static int* optionSlot(const char* name) {
   if (!std::strcmp(name, "encode_slot_words")) return &o.encode_slot_words;
   if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
   if (!std::strcmp(name, "hist_mode")) return &o.hist_mode;
+  if (!std::strcmp(name, "hist_ctas_per_sm")) return &o.hist_ctas_per_sm;
   if (!std::strcmp(name, "timing")) return &o.timing;
   if (!std::strcmp(name, "parts")) return &o.parts;
   return nullptr;

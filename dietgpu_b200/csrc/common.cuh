@@ -65,13 +65,14 @@ struct __align__(16) EncEntry {
 // ---- tuning options (dgb_set_option) ---------------------------------------
 struct Options {
   int decode_stage = 1;      // 1: stream staged into smem with cp.async.bulk (TMA); 0: direct LDG
-  int decode_warps = 4;      // warps per decode CTA (4 or 8)
+  int decode_warps = 8;      // warps per decode CTA (4 or 8)
   int decode_lut64 = 0;      // 1: 8-byte decode LUT entries (fewer ALU ops, more smem)
   int decode_slot_words = 0; // TMA staging slot per warp in u16 words; 0 = auto
   int encode_warps = 8;      // warps per encode CTA (each warp is an independent worker)
   int encode_slot_words = 0; // staging slot of the fast encoder in u16 words; 0 = auto
   int encode_canonical = 0;  // 1: streams packed in block order (byte-identical archives, slower)
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
+  int hist_ctas_per_sm = 32; // stats grid = this many CTAs per SM (each CTA loops over slabs)
   int hist_mode = 0;         // 0: per-warp smem atomics; 1: per-lane private byte counters
   int parts = 0;             // sub-batches run on internal streams (0 = auto, 1 = off, max 4)
   int timing = 0;            // 1: bracket every kernel launch with CUDA events (bench.py roofline pass)

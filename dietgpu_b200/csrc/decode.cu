@@ -30,7 +30,7 @@
 #define DGB_DECODE_UNROLL 8
 #endif
 #ifndef DGB_DECODE_WARPS_PER_SM
-#define DGB_DECODE_WARPS_PER_SM 48
+#define DGB_DECODE_WARPS_PER_SM 40
 #endif
 
 namespace dgb {
@@ -132,8 +132,11 @@ planKernel(DecodeScratch sc, uint32_t m0, uint32_t m1, uint32_t part, int pb,
 // samples were long-scoreboard waits on per-row LDG.U8 of these bytes; holding
 // them in registers instead made ptxas sink the loads next to their use).
 // ---------------------------------------------------------------------------
-constexpr int kGroupRows = 8;       // rows per prefetch group
-constexpr uint32_t kRingSlots = 4;  // groups resident per warp (current + 2 in flight + 1 spare)
+#ifndef DGB_DEC_GROUP_ROWS
+#define DGB_DEC_GROUP_ROWS 16
+#endif
+constexpr int kGroupRows = DGB_DEC_GROUP_ROWS;  // rows per prefetch group (8 or 16)
+constexpr uint32_t kRingSlots = 3;              // groups resident per warp: current + 2 in flight
 
 __device__ __forceinline__ void cpAsync16(uint32_t dstSmem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstSmem), "l"(src) : "memory");
@@ -202,7 +205,7 @@ struct RowWriter16 {
   }
   // request rows [row, row + 8) into ring slot `slot`
   __device__ __forceinline__ void issue(uint32_t row, uint32_t slot) const {
-    if (lane < 16u) cpAsync16(ring + slot * kRingSlotBytes + lane * 16u, nonCopy + row * 32u);
+    if (lane < (uint32_t)(kGroupRows * 2)) cpAsync16(ring + slot * kRingSlotBytes + lane * 16u, nonCopy + row * 32u);
   }
   static __device__ __forceinline__ uint32_t join(uint32_t entry, uint32_t nc) {
     if (KIND == kKindF16) {
@@ -257,8 +260,10 @@ struct RowWriter<kKindF32> {
   }
   __device__ __forceinline__ void issue(uint32_t row, uint32_t slot) const {
     const uint32_t base = ring + slot * kRingSlotBytes;
-    cpAsync16(base + lane * 16u, copy2 + row * 64u);  // 32 lanes x 16 B = 8 rows x 64 B
-    if (lane < 16u) cpAsync16(base + kGroupRows * 64 + lane * 16u, copy1 + row * 32u);
+#pragma unroll
+    for (int h = 0; h < kGroupRows / 8; ++h)  // 32 lanes x 16 B = 8 rows x 64 B per copy
+      cpAsync16(base + h * 512 + lane * 16u, copy2 + row * 64u + h * 512);
+    if (lane < (uint32_t)(kGroupRows * 2)) cpAsync16(base + kGroupRows * 64 + lane * 16u, copy1 + row * 32u);
   }
   static __device__ __forceinline__ uint32_t join(uint32_t entry, uint32_t lo, uint32_t hi) {
     // float/GpuFloatUtils.cuh:187-190: (comp << 24 | stored 24 bits) rotated right by one
@@ -427,14 +432,17 @@ __device__ __forceinline__ void decodeBlockWarp(uint32_t state, Stream st, uint3
     const uint32_t e = decodeStepPartial<PB, LUT64>(valid, state, lut, st, geMask);
     if (valid) wr.writeSlow(row, e);
   }
+  uint32_t slot = 0, slotNext = 2;  // ring slots of group k and of group k + 2
   for (uint32_t k = 0; k < groups; ++k) {
     row -= U;
-    if (k + 2 < groups) wr.issue(row - 2 * U, (k + 2) & (kRingSlots - 1));
+    if (k + 2 < groups) wr.issue(row - 2 * U, slotNext);
     cpAsyncCommit();
     cpAsyncWait<2>();  // group k has landed (the two youngest may still be in flight)
     __syncwarp();
-    const Cursor c = wr.at(row, k & (kRingSlots - 1));
+    const Cursor c = wr.at(row, slot);
     G::run(state, lut, st, geMask, wr, c);
+    slot = slot + 1 == kRingSlots ? 0u : slot + 1;
+    slotNext = slotNext + 1 == kRingSlots ? 0u : slotNext + 1;
   }
   while (row > 0) {
     --row;

@@ -1085,7 +1085,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     const uint64_t maxVecs = ((uint64_t)partMax * elemBytes) / 16u;
     uint32_t gridY = (uint32_t)std::max<uint64_t>(1, (maxVecs + slabVecs - 1) / slabVecs);
     // enough CTAs to fill the machine a few times, never more than the slabs
-    const uint32_t wantY = std::max(1u, (uint32_t)(8 * sms * 4) / (m1 - m0));
+    const uint32_t wantY = std::max(1u, (uint32_t)(std::max(1, opt.hist_ctas_per_sm) * sms) / (m1 - m0));
     gridY = std::min(std::min(gridY, wantY), 65535u);
     dim3 grid1(m1 - m0, gridY);
     timerBegin(kSlotStats, ps);

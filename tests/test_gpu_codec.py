@@ -429,6 +429,6 @@ def test_kernel_variants_agree():
                             capi.set_option("encode_canonical", canon)
                             ans_roundtrip(a, 10)
     finally:
-        for k, v in (("decode_stage", 1), ("decode_warps", 4), ("encode_warps", 8), ("decode_lut64", 0),
+        for k, v in (("decode_stage", 1), ("decode_warps", 8), ("encode_warps", 8), ("decode_lut64", 0),
                      ("encode_canonical", 0)):
             capi.set_option(k, v)
