@@ -502,9 +502,22 @@ def main():
                 roofline_all[k] = {"bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
                                    "frac": round(a / peak, 4), "ms": round(v["ms_avg"], 4),
                                    "algorithmic_bytes": int(alg[k])}
+        # DRAM traffic per launch from the committed `ncu --set full` captures of the same workload
+        # (profiles/r*_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), else null
+        traffic = {}
+        try:
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]
+            for k, v in json.load(open(tf)).items():
+                if v.get("workload") == args.workload:
+                    traffic[k] = int(v["traffic"])
+        except Exception:  # noqa: BLE001
+            pass
+        for k in roofline_all:
+            roofline_all[k]["traffic"] = traffic.get(k)
         dom = max(roofline_all, key=lambda k: roofline_all[k]["ms"])
         roofline = dict(roofline_all[dom])
-        roofline.update({"kernel": dom, "traffic": None, "peak_source": peak_src})
+        roofline.update({"kernel": dom, "peak_source": peak_src})
         # direction-level figures (encode = decode = 2F + C_f algorithmic bytes)
         for d, t in (("encode_direction", main_res["t_enc"]), ("decode_direction", main_res["t_dec"])):
             a = (ubytes + cbytes) * steps / t / 1e9
