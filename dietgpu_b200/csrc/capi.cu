@@ -64,11 +64,16 @@ void splitParts(const uint64_t* weight, uint32_t n, int parts, uint32_t* bounds)
   bounds[parts] = n;
 }
 
-int autoParts(int kind, uint32_t n, uint64_t totalBytes) {
+int autoParts(int kind, uint32_t n, uint64_t totalBytes, bool decode) {
   const Options& o = options();
   if (o.timing) return 1;  // per-kernel timing wants un-overlapped launches
   int p = o.parts;
-  if (p <= 0) p = (kind != kKindBytes && n >= 8 && totalBytes >= (64ull << 20)) ? 2 : 1;
+  // measured on B200 (tools/walltime.py, 256 MiB batches): encode is best with 2 sub-batches (its two
+  // kernels overlap), decode with 4 (plan latency and kernel tails hide); byte inputs gain nothing
+  if (p <= 0) {
+    const bool big = kind != kKindBytes && totalBytes >= (64ull << 20);
+    p = !big ? 1 : (decode ? (n >= 16 ? 4 : (n >= 8 ? 2 : 1)) : (n >= 8 ? 2 : 1));
+  }
   p = std::min(p, kMaxParts);
   return (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)p, n));
 }

@@ -114,7 +114,7 @@ struct StreamPool {
 int streamPool(StreamPool** out);  // lazily created; DGB_OK or DGB_ERR_CUDA
 // cuts members [0,n) into `parts` contiguous ranges of roughly equal `weight`; bounds has parts+1 entries
 void splitParts(const uint64_t* weight, uint32_t n, int parts, uint32_t* bounds);
-int autoParts(int kind, uint32_t n, uint64_t totalBytes);
+int autoParts(int kind, uint32_t n, uint64_t totalBytes, bool decode);
 
 void timerBegin(int slot, cudaStream_t stream);
 void timerEnd(int slot, cudaStream_t stream);

@@ -744,7 +744,7 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   std::vector<uint64_t> weight(n);
   uint64_t totalBytes = 0;
   for (uint32_t i = 0; i < n; ++i) { weight[i] = (uint64_t)desc[i].size * wordBytes; totalBytes += weight[i]; }
-  const int parts = autoParts(kind, n, totalBytes);
+  const int parts = autoParts(kind, n, totalBytes, true);
   uint32_t bounds[kMaxParts + 1];
   splitParts(weight.data(), n, parts, bounds);
   StreamPool* pool = nullptr;

@@ -1029,7 +1029,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   uint64_t totalBytes = 0;
   for (uint32_t i = 0; i < n; ++i) { weight[i] = (uint64_t)desc[i].size * elemBytes; totalBytes += weight[i]; }
   // byte inputs measured slightly slower when split (their stats kernel is atomics-bound, not HBM-bound)
-  const int parts = canonical ? 1 : autoParts(kind, n, totalBytes);
+  const int parts = canonical ? 1 : autoParts(kind, n, totalBytes, false);
   uint32_t bounds[kMaxParts + 1];
   splitParts(weight.data(), n, parts, bounds);
   StreamPool* pool = nullptr;

@@ -1,0 +1,39 @@
+"""Wall (event) time of encode / decode calls for option variants: python tools/walltime.py <wl> 'opt=v,...' ..."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from dietgpu_b200 import capi  # noqa: E402
+
+wl = sys.argv[1]
+kind, batch, per, desc = bench.WORKLOADS[wl]
+ts = bench.make_batch(torch, kind, batch, per, 1234, torch.device("cuda", 0))
+ub = sum(t.numel() * t.element_size() for t in ts)
+it = torch.int16 if kind != "bytes" else torch.uint8
+for v in sys.argv[2:] or [""]:
+    for kv in [x for x in v.split(",") if x]:
+        k, val = kv.split("=")
+        capi.set_option(k, int(val))
+    c = bench.OursCodec(torch, kind, ts)
+    c.encode(); c.bind_rows(); c.decode(); torch.cuda.synchronize()
+    ok = all(torch.equal(a.view(it), b.view(it)) for a, b in zip(ts, c.outs))
+    for _ in range(3):
+        c.encode(); c.decode()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    n = 30
+    e[0].record()
+    for _ in range(n):
+        c.encode()
+    e[1].record()
+    for _ in range(n):
+        c.decode()
+    e[2].record()
+    torch.cuda.synchronize()
+    te, td = e[0].elapsed_time(e[1]) / n * 1e3, e[1].elapsed_time(e[2]) / n * 1e3
+    print(f"{wl} [{v}] ok={ok} enc {te:.1f}us {ub / te / 1e3:.0f} GB/s | dec {td:.1f}us {ub / td / 1e3:.0f} GB/s | both {2 * ub / (te + td) / 1e3:.0f} GB/s", flush=True)
+    del c
