@@ -55,9 +55,10 @@ static_assert(sizeof(MemberDesc) == 24, "");
 
 // ---- encoder symbol table entry (one per symbol, 16 B, shared memory) ------
 // x: thr   = pdf << (31 - pb)      renormalise when state >= thr
-// y: magic                           ans/GpuANSStatistics.cuh:343-358
+// y: magic  = ceil(2^(32+shift)/pdf)  state / pdf == hi32(state * magic) >> shift for state < 2^31
+//                                    (same quotient as ans/GpuANSStatistics.cuh:343-358, no add)
 // z: shift | (2^pb - pdf) << 8       shift in the low byte (used with shf.wrap)
-// w: cdf
+// w: cdf (+ 2^pb - 1 when pdf == 1, see normalizeAndPublish)
 struct __align__(16) EncEntry {
   uint32_t thr, magic, kmpShift, cdf;
 };

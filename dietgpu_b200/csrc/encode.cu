@@ -130,18 +130,25 @@ __device__ void normalizeAndPublish(const uint32_t* __restrict__ histGlobal, uin
   uint32_t totalPdf;
   const uint32_t cdf = blockExclusiveScan<kStatsThreads>(pdf, sWarp, &totalPdf);
 
-  // :343-358 division constants
-  uint32_t shift = pdf > 1 ? 32u - (uint32_t)__clz((int)(pdf - 1)) : 0u;
-  uint32_t magic = 0;
-  if (pdf > 0) {
-    unsigned long long num = (1ull << 32) * ((1ull << shift) - (unsigned long long)pdf);
-    magic = (uint32_t)(num / pdf + 1ull);
+  // Division constants.  The reference (:343-358) uses the round-up magic that needs
+  // hi32(x * magic) + x; the coder state is always < 2^31 here, so the plain round-up
+  // reciprocal M = ceil(2^(32+s) / pdf), s = ceil(log2 pdf) - 1, already gives the exact
+  // quotient as hi32(x * M) >> s (x * (M * pdf - 2^(32+s)) < 2^31 * pdf <= 2^(32+s)), one add
+  // and one register pair cheaper per symbol.  pdf == 1 has no such M below 2^32: it uses
+  // M = 2^32 - 1 (quotient x - 1) and folds the missing (K - 1) into the cdf term.
+  uint32_t shift = 0, magic = 0, cdfTerm = cdf;
+  if (pdf > 1) {
+    shift = 31u - (uint32_t)__clz((int)(pdf - 1));
+    magic = (uint32_t)(((1ull << (32 + shift)) + pdf - 1) / pdf);
+  } else if (pdf == 1) {
+    magic = 0xffffffffu;
+    cdfTerm = cdf + (K - 1u);
   }
   EncEntry e;
   e.thr = pdf << (31 - pb);
   e.magic = magic;
   e.kmpShift = shift | ((K - pdf) << 8);
-  e.cdf = cdf;
+  e.cdf = cdfTerm;
   tableOut[t] = e;
   // archive: u16 pdf[256] right after the 32 B header (ans/GpuANSEncode.cuh:572-577)
   reinterpret_cast<uint16_t*>(ansArchive + kAnsHeaderBytes)[t] = (uint16_t)pdf;
@@ -518,8 +525,7 @@ __device__ __forceinline__ uint4 ldsEntry(uint32_t addr) {
 }
 
 __device__ __forceinline__ void encodeUpdate(uint32_t& state, const uint4& e) {
-  const uint32_t tq = __umulhi(state, e.y);
-  const uint32_t div = __funnelshift_r(tq + state, 0u, e.z);  // shift = e.z & 31
+  const uint32_t div = __funnelshift_r(__umulhi(state, e.y), 0u, e.z);  // shift = e.z & 31
   state = div * (e.z >> 8) + state + e.w;
 }
 
