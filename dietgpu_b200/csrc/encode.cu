@@ -493,27 +493,30 @@ __device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {
 // `wa` is the shared-memory BYTE address of the next free staging word.
 // The emit half is PTX so that one predicate feeds the vote, the store and the
 // shift (the compiler otherwise materialises the comparison twice).
-__device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_t& wa, uint32_t ltMask) {
+__device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_t& wa, uint32_t ltMask,
+                                          uint32_t one) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      ".reg .b32 v, t, a;\n"
+      ".reg .b32 v, t, a, w;\n"
       ".reg .b16 h;\n"
       "setp.ge.u32 p, %0, %2;\n"
+      // The emitted word gets its own register: the store waits for the POPC below, and if it read
+      // the state register the in-place shift (and with it the whole serial chain) would wait too.
+      // The copy is a multiply by an opaque 1 so that it runs on the FMA pipe, not the busier ALU.
+      "mul.lo.u32 w, %0, %4;\n"
+      "@p shr.u32 %0, %0, 16;\n"
       "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
       "and.b32 t, v, %3;\n"
       "popc.b32 t, t;\n"
-      "shl.b32 t, t, 1;\n"
-      "add.u32 a, %1, t;\n"
-      "cvt.u16.u32 h, %0;\n"
+      "mad.lo.u32 a, t, 2, %1;\n"
+      "cvt.u16.u32 h, w;\n"
       "@p st.shared.u16 [a], h;\n"
-      "@p shr.u32 %0, %0, 16;\n"
       "popc.b32 t, v;\n"
-      "shl.b32 t, t, 1;\n"
-      "add.u32 %1, %1, t;\n"
+      "mad.lo.u32 %1, t, 2, %1;\n"
       "}\n"
       : "+r"(state), "+r"(wa)
-      : "r"(thr), "r"(ltMask)
+      : "r"(thr), "r"(ltMask), "r"(one)
       : "memory");
 }
 
@@ -524,25 +527,41 @@ __device__ __forceinline__ uint4 ldsEntry(uint32_t addr) {
   return e;
 }
 
-__device__ __forceinline__ void encodeUpdate(uint32_t& state, const uint4& e) {
-  const uint32_t div = __funnelshift_r(__umulhi(state, e.y), 0u, e.z);  // shift = e.z & 31
-  state = div * (e.z >> 8) + state + e.w;
+// Loop-invariant registers of the row loop.  `one` and `c24` hold 1 and 2^24 but are opaque to the
+// compiler: multiplying by them turns a copy, an add and a right shift into IMAD / IMAD.HI, which
+// issue on the FMA pipe; as LOP3 / IADD3 / SHF they would queue on the ALU pipe, the busiest one
+// in this loop (profiles/r01_prof7_encode_c3.summary.txt).
+struct EncRegs {
+  uint32_t tabAddr, ltMask, one, c24;
+};
+__device__ __forceinline__ EncRegs makeEncRegs(uint32_t tabAddr) {
+  EncRegs r;
+  r.tabAddr = tabAddr;
+  r.ltMask = laneMaskLt();
+  asm volatile("mov.u32 %0, 1;" : "=r"(r.one));
+  asm volatile("mov.u32 %0, 0x1000000;" : "=r"(r.c24));
+  return r;
 }
 
-__device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t sym, uint32_t tabAddr,
-                                           uint32_t& wa, uint32_t ltMask) {
-  const uint4 e = ldsEntry(tabAddr + sym * 16u);
-  emitWords(state, e.x, wa, ltMask);
-  encodeUpdate(state, e);
+__device__ __forceinline__ void encodeUpdate(uint32_t& state, const uint4& e, const EncRegs& rc) {
+  const uint32_t div = __funnelshift_r(__umulhi(state, e.y), 0u, e.z);  // shift = e.z & 31
+  const uint32_t kmp = __umulhi(e.z, rc.c24);                           // e.z >> 8
+  state = div * kmp + (state * rc.one + e.w);
+}
+
+__device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t sym, const EncRegs& rc, uint32_t& wa) {
+  const uint4 e = ldsEntry(rc.tabAddr + sym * 16u);
+  emitWords(state, e.x, wa, rc.ltMask, rc.one);
+  encodeUpdate(state, e, rc);
 }
 
 __device__ __forceinline__ void encodeStepPartial(bool valid, uint32_t& state, uint32_t sym,
-                                                  uint32_t tabAddr, uint32_t& wa, uint32_t ltMask) {
-  const uint4 e = ldsEntry(tabAddr + sym * 16u);
+                                                  const EncRegs& rc, uint32_t& wa) {
+  const uint4 e = ldsEntry(rc.tabAddr + sym * 16u);
   // invalid lanes never emit: compare against an unreachable threshold
-  emitWords(state, valid ? e.x : 0xffffffffu, wa, ltMask);
+  emitWords(state, valid ? e.x : 0xffffffffu, wa, rc.ltMask, rc.one);
   uint32_t next = state;
-  encodeUpdate(next, e);
+  encodeUpdate(next, e, rc);
   state = valid ? next : state;
 }
 
@@ -561,12 +580,12 @@ struct EncLoad<0> {
   static __device__ __forceinline__ void syms(uint32_t, uint32_t, uint32_t*) {}
 };
 
-__device__ __forceinline__ void encodeGroup(uint32_t& state, uint32_t ringLane, uint32_t tabAddr,
-                                            uint32_t& wa, uint32_t ltMask) {
+__device__ __forceinline__ void encodeGroup(uint32_t& state, uint32_t ringLane, const EncRegs& rc,
+                                            uint32_t& wa) {
   constexpr int U = kEncGroupRows;
   constexpr int kDepth = 4;
   uint32_t addr[U];
-  EncLoad<U>::syms(ringLane, tabAddr, addr);
+  EncLoad<U>::syms(ringLane, rc.tabAddr, addr);
   uint4 e[kDepth];
 #pragma unroll
   for (int j = 0; j < kDepth; ++j) e[j] = ldsEntry(addr[j]);
@@ -574,8 +593,8 @@ __device__ __forceinline__ void encodeGroup(uint32_t& state, uint32_t ringLane, 
   for (int j = 0; j < U; ++j) {
     const uint4 cur = e[j % kDepth];
     if (j + kDepth < U) e[j % kDepth] = ldsEntry(addr[j + kDepth]);
-    emitWords(state, cur.x, wa, ltMask);
-    encodeUpdate(state, cur);
+    emitWords(state, cur.x, wa, rc.ltMask, rc.one);
+    encodeUpdate(state, cur, rc);
   }
 }
 
@@ -616,7 +635,7 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
   constexpr int U = kEncGroupRows;
   uint32_t state = kStateMin;
   uint32_t wa = stageAddr;
-  const uint32_t ltMask = laneMaskLt();
+  const EncRegs rc = makeEncRegs(tabAddr);
   const uint32_t fullRows = n >> 5;
   uint32_t r = 0;
   sp.spilled = 0;
@@ -637,7 +656,7 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
       if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
       cpAsyncWait<2>();
       __syncwarp();
-      encodeGroup(state, ringAddr + (k & (kEncRingSlots - 1)) * (U * 32) + lane, tabAddr, wa, ltMask);
+      encodeGroup(state, ringAddr + (k & (kEncRingSlots - 1)) * (U * 32) + lane, rc, wa);
     }
     r = groups * U;
   }
@@ -646,14 +665,14 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
   const uint8_t* p = in + lane + r * 32u;
   for (uint32_t j = 0; r < fullRows; ++r, ++j, p += 32) {
     if (sp.area && (j % U) == 0 && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
-    encodeStep(state, p[0], tabAddr, wa, ltMask);
+    encodeStep(state, p[0], rc, wa);
   }
   const uint32_t rem = n & 31u;
   if (rem) {
     if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
     const bool valid = lane < rem;
     const uint32_t sym = valid ? p[0] : 0u;
-    encodeStepPartial(valid, state, sym, tabAddr, wa, ltMask);
+    encodeStepPartial(valid, state, sym, rc, wa);
   }
   stateOut = state;
   return sp.spilled + ((wa - stageAddr) >> 1);
