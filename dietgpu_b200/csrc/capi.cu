@@ -324,6 +324,7 @@ static int* optionSlot(const char* name) {
   if (!std::strcmp(name, "decode_slot_words")) return &o.decode_slot_words;
   if (!std::strcmp(name, "encode_warps")) return &o.encode_warps;
   if (!std::strcmp(name, "encode_canonical")) return &o.encode_canonical;
+  if (!std::strcmp(name, "encode_wide_table")) return &o.encode_wide_table;
   if (!std::strcmp(name, "encode_slot_words")) return &o.encode_slot_words;
   if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
   if (!std::strcmp(name, "hist_mode")) return &o.hist_mode;

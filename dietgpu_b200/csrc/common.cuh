@@ -53,13 +53,19 @@ struct MemberDesc {
 };
 static_assert(sizeof(MemberDesc) == 24, "");
 
-// ---- encoder symbol table entry (one per symbol, 16 B, shared memory) ------
-// x: thr   = pdf << (31 - pb)      renormalise when state >= thr
-// y: magic  = ceil(2^(32+shift)/pdf)  state / pdf == hi32(state * magic) >> shift for state < 2^31
-//                                    (same quotient as ans/GpuANSStatistics.cuh:343-358, no add)
-// z: shift | (2^pb - pdf) << 8       shift in the low byte (used with shf.wrap)
-// w: cdf (+ 2^pb - 1 when pdf == 1, see normalizeAndPublish)
-struct __align__(16) EncEntry {
+// ---- encoder symbol table entry (one per symbol, 8 B, shared memory) -------
+// magic = ceil(2^(32+shift)/pdf): state / pdf == hi32(state * magic) >> shift for state < 2^31
+//         (the quotient ans/GpuANSStatistics.cuh:343-358 computes, without its add; pdf == 1 uses
+//         2^32 - 1, i.e. state - 1, and carries the missing 2^pb - 1 in the cdf term)
+// pack  = shift (bits 0..4, consumed by shf.wrap) | 2^pb - pdf (bits 5..16) | cdf term (bits 20..31)
+// The renormalisation threshold pdf << (31 - pb) is rebuilt from 2^pb - pdf (encode.cu ldsEntry).
+struct __align__(8) EncEntry {
+  uint32_t magic, pack;
+};
+constexpr uint32_t kEncKmpShift = 5, kEncCdfShift = 20;
+// Wide form of the same entry: nothing to unpack, four wavefronts per lookup (see EncSym in encode.cu).
+//   thr = pdf << (31 - pb), kmpShift = shift | (2^pb - pdf) << 8, cdf = cdf term
+struct __align__(16) EncEntryWide {
   uint32_t thr, magic, kmpShift, cdf;
 };
 
@@ -72,6 +78,7 @@ struct Options {
   int encode_warps = 8;      // warps per encode CTA (each warp is an independent worker)
   int encode_slot_words = 0; // staging slot of the fast encoder in u16 words; 0 = auto
   int encode_canonical = 0;  // 1: streams packed in block order (byte-identical archives, slower)
+  int encode_wide_table = -1;  // encoder table entries: 1 = 16 B, 0 = 8 B, -1 = by data kind (bf16/fp32 wide)
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_ctas_per_sm = 32; // stats grid = this many CTAs per SM (each CTA loops over slabs)
   int hist_mode = 0;         // 0: per-warp smem atomics; 1: per-lane private byte counters

@@ -52,7 +52,8 @@ struct EncodeScratch {
   unsigned long long* lookback;   // [totalTickets](zeroed)   canonical (ordered) layout only
   unsigned long long* allocDone;  // [n]           (zeroed)   low: words handed out, high: blocks placed
   uint8_t* spill;                 // [resident warps][maxBlockWords] u16: overflow of small staging slots
-  EncEntry* table;                // [n][256]
+  uint4* table;                   // [n][256] slots of 16 B (packed entries use the first half)
+  bool wideTable;                 // entry format: EncEntryWide (16 B) or EncEntry (8 B)
   uint8_t* compRows;              // float kinds: [n] rows of compStride bytes
   uint32_t compStride;
 };
@@ -63,7 +64,7 @@ struct EncodeScratch {
 // rank-by-counting over the 256 unique keys (q << 16 | sym), descending.
 // ---------------------------------------------------------------------------
 __device__ void normalizeAndPublish(const uint32_t* __restrict__ histGlobal, uint32_t total,
-                                    int pb, EncEntry* __restrict__ tableOut,
+                                    int pb, bool wideTable, uint4* __restrict__ tableOut,
                                     uint8_t* __restrict__ ansArchive) {
   __shared__ uint32_t sKey[kNumSymbols];
   __shared__ uint32_t sQByRank[kNumSymbols];
@@ -144,12 +145,19 @@ __device__ void normalizeAndPublish(const uint32_t* __restrict__ histGlobal, uin
     magic = 0xffffffffu;
     cdfTerm = cdf + (K - 1u);
   }
-  EncEntry e;
-  e.thr = pdf << (31 - pb);
-  e.magic = magic;
-  e.kmpShift = shift | ((K - pdf) << 8);
-  e.cdf = cdfTerm;
-  tableOut[t] = e;
+  if (wideTable) {
+    EncEntryWide e;
+    e.thr = pdf << (31 - pb);
+    e.magic = magic;
+    e.kmpShift = shift | ((K - pdf) << 8);
+    e.cdf = cdfTerm;
+    reinterpret_cast<EncEntryWide*>(tableOut)[t] = e;
+  } else {
+    EncEntry e;
+    e.magic = magic;
+    e.pack = shift | ((K - pdf) << kEncKmpShift) | (cdfTerm << kEncCdfShift);
+    reinterpret_cast<EncEntry*>(tableOut)[t] = e;
+  }
   // archive: u16 pdf[256] right after the 32 B header (ans/GpuANSEncode.cuh:572-577)
   reinterpret_cast<uint16_t*>(ansArchive + kAnsHeaderBytes)[t] = (uint16_t)pdf;
 }
@@ -276,7 +284,7 @@ statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, 
     return;
   }
   const uint32_t* h = doHist ? sc.hist + m * kNumSymbols : histogramGiven + m * kNumSymbols;
-  normalizeAndPublish(h, size, pb, sc.table + m * kNumSymbols, archive);
+  normalizeAndPublish(h, size, pb, sc.wideTable, sc.table + m * kNumSymbols, archive);
 }
 
 // ---------------------------------------------------------------------------
@@ -452,7 +460,7 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
   if (useChecksum && t == 0) {
     reinterpret_cast<uint32_t*>(archive)[3] = __ldcg(sc.checksum + m);
   }
-  normalizeAndPublish(sc.hist + m * kNumSymbols, size, pb, sc.table + m * kNumSymbols, ansArchive);
+  normalizeAndPublish(sc.hist + m * kNumSymbols, size, pb, sc.wideTable, sc.table + m * kNumSymbols, ansArchive);
 }
 
 // ---------------------------------------------------------------------------
@@ -493,8 +501,7 @@ __device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {
 // `wa` is the shared-memory BYTE address of the next free staging word.
 // The emit half is PTX so that one predicate feeds the vote, the store and the
 // shift (the compiler otherwise materialises the comparison twice).
-__device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_t& wa, uint32_t ltMask,
-                                          uint32_t one) {
+__device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_t& wa, uint32_t ltMask) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -503,9 +510,9 @@ __device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_
       "setp.ge.u32 p, %0, %2;\n"
       // The emitted word gets its own register: the store waits for the POPC below, and if it read
       // the state register the in-place shift (and with it the whole serial chain) would wait too.
-      // The copy is a multiply by an opaque 1 so that it runs on the FMA pipe, not the busier ALU.
-      "mul.lo.u32 w, %0, %4;\n"
-      "@p shr.u32 %0, %0, 16;\n"
+      "mov.b32 w, %0;\n"
+      "shr.u32 t, %0, 16;\n"
+      "selp.b32 %0, t, %0, p;\n"
       "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
       "and.b32 t, v, %3;\n"
       "popc.b32 t, t;\n"
@@ -516,85 +523,116 @@ __device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_
       "mad.lo.u32 %1, t, 2, %1;\n"
       "}\n"
       : "+r"(state), "+r"(wa)
-      : "r"(thr), "r"(ltMask), "r"(one)
+      : "r"(thr), "r"(ltMask)
       : "memory");
 }
 
-__device__ __forceinline__ uint4 ldsEntry(uint32_t addr) {
-  uint4 e;
-  // not volatile: the table is read-only while a block is encoded, so the scheduler may hoist it
-  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(addr));
-  return e;
-}
-
-// Loop-invariant registers of the row loop.  `one` and `c24` hold 1 and 2^24 but are opaque to the
-// compiler: multiplying by them turns a copy, an add and a right shift into IMAD / IMAD.HI, which
-// issue on the FMA pipe; as LOP3 / IADD3 / SHF they would queue on the ALU pipe, the busiest one
-// in this loop (profiles/r01_prof7_encode_c3.summary.txt).
+// Table entry -> the values a row needs.  Two formats (common.cuh), chosen per call by what the
+// ANS input is:
+//  * EncEntryWide (16 B, LDS.128, four shared-memory wavefronts per row): every field is stored, the
+//    row needs the fewest instructions.  Right when a row touches few distinct symbols, i.e. the
+//    exponent bytes of bf16 / fp32 data (mostly broadcast reads).
+//  * EncEntry (8 B, LDS.64, two wavefronts): the threshold pdf << (31 - pb) is rebuilt from 2^pb - pdf
+//    with one multiply-add and the fields are unpacked with multiplies (IMAD.SHL / IMAD.HI issue on
+//    the FMA pipe; the ALU pipe is the busy one here).  Right for byte data and fp16, where the
+//    bank conflicts of the wide entry dominate (c2: 371 -> 270 us, c4: 162 -> 144 us; c3 128 vs 140).
+// Everything here is independent of the coder state, so it runs ahead of the serial chain.
 struct EncRegs {
-  uint32_t tabAddr, ltMask, one, c24;
+  uint32_t tabAddr, ltMask, thrNegScale;  // thrNegScale = -(2^(31 - pb)), packed format only
 };
-__device__ __forceinline__ EncRegs makeEncRegs(uint32_t tabAddr) {
+__device__ __forceinline__ EncRegs makeEncRegs(uint32_t tabAddr, int pb) {
   EncRegs r;
   r.tabAddr = tabAddr;
   r.ltMask = laneMaskLt();
-  asm volatile("mov.u32 %0, 1;" : "=r"(r.one));
-  asm volatile("mov.u32 %0, 0x1000000;" : "=r"(r.c24));
+  r.thrNegScale = 0u - (1u << (31 - pb));
   return r;
 }
 
-__device__ __forceinline__ void encodeUpdate(uint32_t& state, const uint4& e, const EncRegs& rc) {
-  const uint32_t div = __funnelshift_r(__umulhi(state, e.y), 0u, e.z);  // shift = e.z & 31
-  const uint32_t kmp = __umulhi(e.z, rc.c24);                           // e.z >> 8
-  state = div * kmp + (state * rc.one + e.w);
+template <bool WIDE>
+struct EncSym;
+template <>
+struct EncSym<true> {
+  static constexpr uint32_t kStride = 16;
+  uint32_t thr, magic, kmpShift, cdf;
+  __device__ __forceinline__ void load(uint32_t addr, const EncRegs&) {
+    // not volatile: the table is read-only while a block is encoded, so the scheduler may hoist it
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(thr), "=r"(magic), "=r"(kmpShift), "=r"(cdf) : "r"(addr));
+  }
+  __device__ __forceinline__ uint32_t shiftReg() const { return kmpShift; }               // low 5 bits count
+  __device__ __forceinline__ uint32_t kmp() const { return __umulhi(kmpShift, 1u << 24); }  // >> 8, FMA pipe
+  __device__ __forceinline__ uint32_t plusCdf(uint32_t x) const { return x + cdf; }
+};
+template <>
+struct EncSym<false> {
+  static constexpr uint32_t kStride = 8;
+  uint32_t thr, magic, pack, kmpv;
+  __device__ __forceinline__ void load(uint32_t addr, const EncRegs& rc) {
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(magic), "=r"(pack) : "r"(addr));
+    kmpv = __umulhi(pack << (32 - kEncCdfShift), 1u << (kEncCdfShift - kEncKmpShift));  // bits 5..19
+    thr = kmpv * rc.thrNegScale + 0x80000000u;                                          // pdf << (31 - pb)
+  }
+  __device__ __forceinline__ uint32_t shiftReg() const { return pack; }
+  __device__ __forceinline__ uint32_t kmp() const { return kmpv; }
+  __device__ __forceinline__ uint32_t plusCdf(uint32_t x) const { return x + (pack >> kEncCdfShift); }
+};
+
+template <bool WIDE>
+__device__ __forceinline__ void encodeUpdate(uint32_t& state, const EncSym<WIDE>& e) {
+  const uint32_t div = __funnelshift_r(__umulhi(state, e.magic), 0u, e.shiftReg());
+  state = div * e.kmp() + e.plusCdf(state);
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t sym, const EncRegs& rc, uint32_t& wa) {
-  const uint4 e = ldsEntry(rc.tabAddr + sym * 16u);
-  emitWords(state, e.x, wa, rc.ltMask, rc.one);
-  encodeUpdate(state, e, rc);
+  EncSym<WIDE> e;
+  e.load(rc.tabAddr + sym * EncSym<WIDE>::kStride, rc);
+  emitWords(state, e.thr, wa, rc.ltMask);
+  encodeUpdate(state, e);
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void encodeStepPartial(bool valid, uint32_t& state, uint32_t sym,
                                                   const EncRegs& rc, uint32_t& wa) {
-  const uint4 e = ldsEntry(rc.tabAddr + sym * 16u);
+  EncSym<WIDE> e;
+  e.load(rc.tabAddr + sym * EncSym<WIDE>::kStride, rc);
   // invalid lanes never emit: compare against an unreachable threshold
-  emitWords(state, valid ? e.x : 0xffffffffu, wa, rc.ltMask, rc.one);
+  emitWords(state, valid ? e.thr : 0xffffffffu, wa, rc.ltMask);
   uint32_t next = state;
-  encodeUpdate(next, e, rc);
+  encodeUpdate(next, e);
   state = valid ? next : state;
 }
 
 // One group of kEncGroupRows rows.  The symbol bytes and the table entries do not depend on
 // the coder state, so they are fetched ahead of the serial state chain: all symbols of the
 // group first, then table entries kept kDepth rows ahead of the row being coded.
-template <int J>
+template <int J, uint32_t STRIDE>
 struct EncLoad {
   static __device__ __forceinline__ void syms(uint32_t ringLane, uint32_t tabAddr, uint32_t* addr) {
-    EncLoad<J - 1>::syms(ringLane, tabAddr, addr);
-    addr[J - 1] = tabAddr + 16u * ldsU8<(J - 1) * 32>(ringLane);
+    EncLoad<J - 1, STRIDE>::syms(ringLane, tabAddr, addr);
+    addr[J - 1] = tabAddr + STRIDE * ldsU8<(J - 1) * 32>(ringLane);
   }
 };
-template <>
-struct EncLoad<0> {
+template <uint32_t STRIDE>
+struct EncLoad<0, STRIDE> {
   static __device__ __forceinline__ void syms(uint32_t, uint32_t, uint32_t*) {}
 };
 
+template <bool WIDE>
 __device__ __forceinline__ void encodeGroup(uint32_t& state, uint32_t ringLane, const EncRegs& rc,
                                             uint32_t& wa) {
   constexpr int U = kEncGroupRows;
   constexpr int kDepth = 4;
   uint32_t addr[U];
-  EncLoad<U>::syms(ringLane, rc.tabAddr, addr);
-  uint4 e[kDepth];
+  EncLoad<U, EncSym<WIDE>::kStride>::syms(ringLane, rc.tabAddr, addr);
+  EncSym<WIDE> e[kDepth];
 #pragma unroll
-  for (int j = 0; j < kDepth; ++j) e[j] = ldsEntry(addr[j]);
+  for (int j = 0; j < kDepth; ++j) e[j].load(addr[j], rc);
 #pragma unroll
   for (int j = 0; j < U; ++j) {
-    const uint4 cur = e[j % kDepth];
-    if (j + kDepth < U) e[j % kDepth] = ldsEntry(addr[j + kDepth]);
-    emitWords(state, cur.x, wa, rc.ltMask, rc.one);
-    encodeUpdate(state, cur, rc);
+    const EncSym<WIDE> cur = e[j % kDepth];
+    if (j + kDepth < U) e[j % kDepth].load(addr[j + kDepth], rc);
+    emitWords(state, cur.thr, wa, rc.ltMask);
+    encodeUpdate(state, cur);
   }
 }
 
@@ -627,15 +665,16 @@ __device__ __forceinline__ void spillOut(Spill& sp, uint32_t stageAddr, uint16_t
 // Encodes bytes [0, n) of one block with one warp into the staging slot at
 // shared byte address `stageAddr` (spilling to sp.area when the slot is small).
 // Returns the TOTAL word count; the words not yet spilled are stage[0 .. total - sp.spilled).
+template <bool WIDE>
 __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ in, uint32_t n,
-                                                    uint32_t tabAddr, uint32_t stageAddr,
+                                                    uint32_t tabAddr, int pb, uint32_t stageAddr,
                                                     uint16_t* stage, Spill& sp,
                                                     uint32_t ringAddr, uint32_t lane,
                                                     uint32_t& stateOut) {
   constexpr int U = kEncGroupRows;
   uint32_t state = kStateMin;
   uint32_t wa = stageAddr;
-  const EncRegs rc = makeEncRegs(tabAddr);
+  const EncRegs rc = makeEncRegs(tabAddr, pb);
   const uint32_t fullRows = n >> 5;
   uint32_t r = 0;
   sp.spilled = 0;
@@ -656,7 +695,7 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
       if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
       cpAsyncWait<2>();
       __syncwarp();
-      encodeGroup(state, ringAddr + (k & (kEncRingSlots - 1)) * (U * 32) + lane, rc, wa);
+      encodeGroup<WIDE>(state, ringAddr + (k & (kEncRingSlots - 1)) * (U * 32) + lane, rc, wa);
     }
     r = groups * U;
   }
@@ -665,14 +704,14 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
   const uint8_t* p = in + lane + r * 32u;
   for (uint32_t j = 0; r < fullRows; ++r, ++j, p += 32) {
     if (sp.area && (j % U) == 0 && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
-    encodeStep(state, p[0], rc, wa);
+    encodeStep<WIDE>(state, p[0], rc, wa);
   }
   const uint32_t rem = n & 31u;
   if (rem) {
     if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
     const bool valid = lane < rem;
     const uint32_t sym = valid ? p[0] : 0u;
-    encodeStepPartial(valid, state, sym, rc, wa);
+    encodeStepPartial<WIDE>(valid, state, sym, rc, wa);
   }
   stateOut = state;
   return sp.spilled + ((wa - stageAddr) >> 1);
@@ -723,9 +762,9 @@ __device__ __forceinline__ uint32_t lookbackWarp(volatile unsigned long long* de
   return base;
 }
 
-// dynamic shared memory per warp: [table 4 KiB][input ring 2 KiB][staging slot]
+// dynamic shared memory per warp: [table 2 KiB][input ring 2 KiB][staging slot]
 __host__ __device__ constexpr uint32_t encWarpSmem(int pb) {
-  return kNumSymbols * 16u + kEncRingSlots * kEncGroupRows * 32u + maxBlockWords(pb) * 2u;
+  return kNumSymbols * 8u + kEncRingSlots * kEncGroupRows * 32u + maxBlockWords(pb) * 2u;
 }
 
 __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksum,
@@ -738,8 +777,8 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
   uint8_t* mine = smem + (size_t)warp * encWarpSmem(pb);
   uint4* myTab = reinterpret_cast<uint4*>(mine);
   const uint32_t tabAddr = smemAddr(mine);
-  const uint32_t ringAddr = tabAddr + kNumSymbols * 16u;
-  uint16_t* myStage = reinterpret_cast<uint16_t*>(mine + kNumSymbols * 16u + kEncRingSlots * kEncGroupRows * 32u);
+  const uint32_t ringAddr = tabAddr + kNumSymbols * 8u;
+  uint16_t* myStage = reinterpret_cast<uint16_t*>(mine + kNumSymbols * 8u + kEncRingSlots * kEncGroupRows * 32u);
   const uint32_t stageAddr = smemAddr(myStage);
   volatile unsigned long long* desc = sc.lookback;
   uint32_t curMember = 0xffffffffu;
@@ -777,9 +816,9 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
 
     if (m != curMember) {
       // this member's encoder table -> my private copy (written by K1's epilogue)
-      const uint4* src = reinterpret_cast<const uint4*>(sc.table + (size_t)m * kNumSymbols);
+      const uint4* src = sc.table + (size_t)m * kNumSymbols;
 #pragma unroll
-      for (uint32_t i = 0; i < kNumSymbols / 32; ++i) myTab[i * 32 + lane] = __ldcg(src + i * 32 + lane);
+      for (uint32_t i = 0; i < kNumSymbols / 64; ++i) myTab[i * 32 + lane] = __ldcg(src + i * 32 + lane);
       curMember = m;
       __syncwarp();
     }
@@ -789,7 +828,7 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
     const uint32_t blockLen = min(kBlockBytes, size - start);
     uint32_t state;
     Spill sp{nullptr, 0u, 0u};  // worst-case sized slot: never spills
-    const uint32_t words = encodeBlockWarp(ansIn + start, blockLen, tabAddr, stageAddr, myStage, sp, ringAddr, lane, state);
+    const uint32_t words = encodeBlockWarp<false>(ansIn + start, blockLen, tabAddr, pb, stageAddr, myStage, sp, ringAddr, lane, state);
     const uint32_t padded = roundUp(words, 8u);
 
     // ---- packed offset of this block: look-back over the member's earlier tickets ----
@@ -844,13 +883,14 @@ __host__ __device__ constexpr uint32_t encFastWarpSmem(uint32_t slotWords) {
   return kEncRingSlots * kEncGroupRows * 32u + slotWords * 2u;  // ring + staging
 }
 
+template <bool WIDE>
 __global__ void
 encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
                                  uint32_t numMembers, uint32_t blockBegin, uint32_t blockEnd,
                                  uint32_t slotWords, uint32_t spillWarpBase,
                                  uint32_t* __restrict__ outSize) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ __align__(16) uint4 sTab[kNumSymbols];  // static: constant base for the hot LDS.128
+  __shared__ __align__(16) uint4 sTab[WIDE ? kNumSymbols : kNumSymbols / 2];  // static: constant base for the hot LDS
   __shared__ uint32_t sMember;
   const uint32_t t = threadIdx.x, lane = t & 31u;
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
@@ -887,8 +927,8 @@ encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
     const uint32_t nb = divUp(size, kBlockBytes);
     const uint32_t memberEnd = min(end, md.work0 + nb);
     {
-      const uint4* src = reinterpret_cast<const uint4*>(sc.table + (size_t)m * kNumSymbols);
-      for (uint32_t i = t; i < kNumSymbols; i += blockDim.x) sTab[i] = __ldcg(src + i);
+      const uint4* src = sc.table + (size_t)m * kNumSymbols;
+      for (uint32_t i = t; i < (WIDE ? kNumSymbols : kNumSymbols / 2); i += blockDim.x) sTab[i] = __ldcg(src + i);
     }
     __syncthreads();
 
@@ -914,7 +954,7 @@ encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
       const uint32_t start = block * kBlockBytes;
       const uint32_t blockLen = min(kBlockBytes, size - start);
       uint32_t state;
-      const uint32_t words = encodeBlockWarp(ansIn + start, blockLen, tabAddr, stageAddr, myStage, sp, ringAddr, lane, state);
+      const uint32_t words = encodeBlockWarp<WIDE>(ansIn + start, blockLen, tabAddr, pb, stageAddr, myStage, sp, ringAddr, lane, state);
       const uint32_t padded = roundUp(words, 8u);
       // take a place in the data section: one 64-bit atomic hands out the word offset (low half)
       // and counts finished blocks (high half), so no fence is needed to order the two
@@ -966,7 +1006,7 @@ ScratchPlan planScratch(int kind, uint32_t n, uint32_t maxSize, uint32_t totalTi
   p.allocDone = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)n);
   p.lookback = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)totalTickets);
   p.zeroEnd = o;
-  p.table = o; o = alignUp256(o + sizeof(EncEntry) * kNumSymbols * (size_t)n);
+  p.table = o; o = alignUp256(o + sizeof(uint4) * kNumSymbols * (size_t)n);
   p.spill = o; o = alignUp256(o + (size_t)kMaxSpillWarps * maxBlockWords(11) * 2u);
   p.compStride = kind == kKindBytes ? 0u : roundUp(maxSize, 16u);
   p.compRows = o; o = alignUp256(o + (size_t)p.compStride * n);
@@ -1037,7 +1077,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   sc.lookback = reinterpret_cast<unsigned long long*>(base + sp.lookback);
   sc.allocDone = reinterpret_cast<unsigned long long*>(base + sp.allocDone);
   sc.spill = base + sp.spill;
-  sc.table = reinterpret_cast<EncEntry*>(base + sp.table);
+  sc.table = reinterpret_cast<uint4*>(base + sp.table);
   sc.compRows = base + sp.compRows;
   sc.compStride = sp.compStride;
 
@@ -1048,6 +1088,10 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   const int sms = smCount();
   const uint32_t elemBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
   const bool canonical = opt.encode_canonical != 0;
+  // encoder table format (see EncSym in this file): wide entries for exponent-byte planes
+  const bool wideTable = !canonical && opt.encode_wide_table != 0 &&
+                         (opt.encode_wide_table > 0 || kind == DGB_BFLOAT16 || kind == DGB_FLOAT32);
+  sc.wideTable = wideTable;
 
   // ---- sub-batches on internal streams (the ordered canonical encoder stays on one stream) ----
   std::vector<uint64_t> weight(n);
@@ -1073,24 +1117,29 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   static bool configured = false;
   if (!configured) {
     DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     configured = true;
   }
   static size_t occKeySmem = 0;
   static uint32_t occKeyW = 0;
   static int occKeyCanon = -1;
   static int perSm = 1;
-  if (occKeySmem != smemBytes || occKeyW != W || occKeyCanon != (int)canonical) {
+  // 0: canonical kernel (packed table), 1: fast kernel + packed table, 2: fast kernel + wide table
+  const int variant = canonical ? 0 : (wideTable ? 2 : 1);
+  if (occKeySmem != smemBytes || occKeyW != W || occKeyCanon != variant) {
     int occ = 0;
-    if (canonical) {
+    if (variant == 0) {
       DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel, (int)(W * 32), smemBytes));
+    } else if (variant == 1) {
+      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast<false>, (int)(W * 32), smemBytes));
     } else {
-      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast, (int)(W * 32), smemBytes));
+      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast<true>, (int)(W * 32), smemBytes));
     }
     perSm = std::max(occ, 1);
     occKeySmem = smemBytes;
     occKeyW = W;
-    occKeyCanon = (int)canonical;
+    occKeyCanon = variant;
   }
   const uint64_t resident = (uint64_t)perSm * sms;
   const uint32_t spillWarpsPerPart = kMaxSpillWarps / (uint32_t)parts;
@@ -1141,8 +1190,13 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
         const uint64_t want = ((uint64_t)partBlocks + W * rounds - 1) / (W * rounds);
         uint32_t grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
         grid2 = std::max(1u, std::min(grid2, spillWarpsPerPart / W));  // every warp owns a spill slot
-        encodeKernelFast<<<grid2, W * 32, smemBytes, ps>>>(sc, kind, pb, checksum, n, blockBegin, blockEnd, slotWords,
-                                                         (uint32_t)part * spillWarpsPerPart, outSize_dev);
+        if (wideTable) {
+          encodeKernelFast<true><<<grid2, W * 32, smemBytes, ps>>>(sc, kind, pb, checksum, n, blockBegin, blockEnd, slotWords,
+                                                                 (uint32_t)part * spillWarpsPerPart, outSize_dev);
+        } else {
+          encodeKernelFast<false><<<grid2, W * 32, smemBytes, ps>>>(sc, kind, pb, checksum, n, blockBegin, blockEnd, slotWords,
+                                                                  (uint32_t)part * spillWarpsPerPart, outSize_dev);
+        }
       }
       DGB_CUDA_TRY(cudaGetLastError());
       timerEnd(kSlotEncode, ps);

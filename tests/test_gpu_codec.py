@@ -411,6 +411,23 @@ def test_sub_batch_streams():
         capi.set_option("parts", 0)
 
 
+def test_encoder_table_formats():
+    # the encoder symbol table has a 16-byte and an 8-byte entry format (chosen by data kind);
+    # force each one on every kind, all precisions, incl. pdf == 1 symbols and a single-symbol input
+    from dietgpu_b200 import capi
+
+    try:
+        for wide in (0, 1):
+            capi.set_option("encode_wide_table", wide)
+            for pb in (9, 10, 11):
+                ans_roundtrip([zipf_bytes(200000, 1.0, 1), exp_bytes(4097, 3, 2), np.full(5000, 7, np.uint8),
+                               np.random.default_rng(3).integers(0, 256, 70001, dtype=np.uint8)], pb, checksum=True)
+            for ft in ("f16", "bf16", "f32"):
+                float_roundtrip(ft, [normal_words(100000 + 7 * i, ft, i) for i in range(3)], 10, checksum=True)
+    finally:
+        capi.set_option("encode_wide_table", -1)
+
+
 def test_kernel_variants_agree():
     # every tuning variant produces identical results
     from dietgpu_b200 import capi
