@@ -62,7 +62,7 @@ static_assert(sizeof(MemberDesc) == 24, "");
 struct __align__(8) EncEntry {
   uint32_t magic, pack;
 };
-constexpr uint32_t kEncKmpShift = 5, kEncCdfShift = 20;
+constexpr uint32_t kEncKmpShift = 5, kEncKmpMask = 0xfffu, kEncCdfShift = 20;
 // Wide form of the same entry: nothing to unpack, four wavefronts per lookup (see EncSym in encode.cu).
 //   thr = pdf << (31 - pb), kmpShift = shift | (2^pb - pdf) << 8, cdf = cdf term
 struct __align__(16) EncEntryWide {

@@ -533,9 +533,10 @@ __device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_
 //    row needs the fewest instructions.  Right when a row touches few distinct symbols, i.e. the
 //    exponent bytes of bf16 / fp32 data (mostly broadcast reads).
 //  * EncEntry (8 B, LDS.64, two wavefronts): the threshold pdf << (31 - pb) is rebuilt from 2^pb - pdf
-//    with one multiply-add and the fields are unpacked with multiplies (IMAD.SHL / IMAD.HI issue on
-//    the FMA pipe; the ALU pipe is the busy one here).  Right for byte data and fp16, where the
-//    bank conflicts of the wide entry dominate (c2: 371 -> 270 us, c4: 162 -> 144 us; c3 128 vs 140).
+//    with one multiply-add and the fields are unpacked with shifts and masks.  Right for byte data
+//    and fp16, where the bank conflicts of the wide entry dominate (c2: 371 -> 266 us, c4: 162 ->
+//    142 us; on c3 the wide entry wins, 126 vs 140 us).
+// (Unpacking with IMAD.HI to move work from the ALU to the FMA pipe was measured slower.)
 // Everything here is independent of the coder state, so it runs ahead of the serial chain.
 struct EncRegs {
   uint32_t tabAddr, ltMask, thrNegScale;  // thrNegScale = -(2^(31 - pb)), packed format only
@@ -559,7 +560,7 @@ struct EncSym<true> {
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(thr), "=r"(magic), "=r"(kmpShift), "=r"(cdf) : "r"(addr));
   }
   __device__ __forceinline__ uint32_t shiftReg() const { return kmpShift; }               // low 5 bits count
-  __device__ __forceinline__ uint32_t kmp() const { return __umulhi(kmpShift, 1u << 24); }  // >> 8, FMA pipe
+  __device__ __forceinline__ uint32_t kmp() const { return kmpShift >> 8; }
   __device__ __forceinline__ uint32_t plusCdf(uint32_t x) const { return x + cdf; }
 };
 template <>
@@ -568,7 +569,7 @@ struct EncSym<false> {
   uint32_t thr, magic, pack, kmpv;
   __device__ __forceinline__ void load(uint32_t addr, const EncRegs& rc) {
     asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(magic), "=r"(pack) : "r"(addr));
-    kmpv = __umulhi(pack << (32 - kEncCdfShift), 1u << (kEncCdfShift - kEncKmpShift));  // bits 5..19
+    kmpv = (pack >> kEncKmpShift) & kEncKmpMask;
     thr = kmpv * rc.thrNegScale + 0x80000000u;                                          // pdf << (31 - pb)
   }
   __device__ __forceinline__ uint32_t shiftReg() const { return pack; }
