@@ -64,9 +64,9 @@ struct __align__(8) EncEntry {
 };
 constexpr uint32_t kEncKmpShift = 5, kEncKmpMask = 0xfffu, kEncCdfShift = 20;
 // Wide form of the same entry: nothing to unpack, four wavefronts per lookup (see EncSym in encode.cu).
-//   thr = pdf << (31 - pb), kmpShift = shift | (2^pb - pdf) << 8, cdf = cdf term
+//   thr = pdf << (31 - pb), kmp = 2^pb - pdf, cdfShift = shift | cdf term << 5
 struct __align__(16) EncEntryWide {
-  uint32_t thr, magic, kmpShift, cdf;
+  uint32_t thr, magic, kmp, cdfShift;
 };
 
 // ---- tuning options (dgb_set_option) ---------------------------------------

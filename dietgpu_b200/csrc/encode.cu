@@ -149,8 +149,8 @@ __device__ void normalizeAndPublish(const uint32_t* __restrict__ histGlobal, uin
     EncEntryWide e;
     e.thr = pdf << (31 - pb);
     e.magic = magic;
-    e.kmpShift = shift | ((K - pdf) << 8);
-    e.cdf = cdfTerm;
+    e.kmp = K - pdf;
+    e.cdfShift = shift | (cdfTerm << 5);
     reinterpret_cast<EncEntryWide*>(tableOut)[t] = e;
   } else {
     EncEntry e;
@@ -501,30 +501,59 @@ __device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {
 // `wa` is the shared-memory BYTE address of the next free staging word.
 // The emit half is PTX so that one predicate feeds the vote, the store and the
 // shift (the compiler otherwise materialises the comparison twice).
-__device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_t& wa, uint32_t ltMask) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b32 v, t, a, w;\n"
-      ".reg .b16 h;\n"
-      "setp.ge.u32 p, %0, %2;\n"
-      // The emitted word gets its own register: the store waits for the POPC below, and if it read
-      // the state register the in-place shift (and with it the whole serial chain) would wait too.
-      "mov.b32 w, %0;\n"
-      "shr.u32 t, %0, 16;\n"
-      "selp.b32 %0, t, %0, p;\n"
-      "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
-      "and.b32 t, v, %3;\n"
-      "popc.b32 t, t;\n"
-      "mad.lo.u32 a, t, 2, %1;\n"
-      "cvt.u16.u32 h, w;\n"
-      "@p st.shared.u16 [a], h;\n"
-      "popc.b32 t, v;\n"
-      "mad.lo.u32 %1, t, 2, %1;\n"
-      "}\n"
-      : "+r"(state), "+r"(wa)
-      : "r"(thr), "r"(ltMask)
-      : "memory");
+// The emitted word gets its own register: the store waits for the POPC, and if it read the state
+// register the in-place shift (and with it the whole serial chain) would wait too.  Two ways to
+// make the copy, picked per table format by measurement (tools/sweep.py, K2 us, c3 / c2 / c4):
+//   FMACOPY = false: plain copy, which ptxas folds into shift + select        (wide 124, packed 266 / 142)
+//   FMACOPY = true : multiply by a 1 the compiler cannot see through (IMAD, FMA pipe) and shift the
+//                    state in place under the predicate                        (wide 131, packed 259 / 137)
+template <bool FMACOPY>
+__device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_t& wa, uint32_t ltMask,
+                                          uint32_t one) {
+  if (FMACOPY) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 v, t, a, w;\n"
+        ".reg .b16 h;\n"
+        "setp.ge.u32 p, %0, %2;\n"
+        "mul.lo.u32 w, %0, %4;\n"
+        "@p shr.u32 %0, %0, 16;\n"
+        "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+        "and.b32 t, v, %3;\n"
+        "popc.b32 t, t;\n"
+        "mad.lo.u32 a, t, 2, %1;\n"
+        "cvt.u16.u32 h, w;\n"
+        "@p st.shared.u16 [a], h;\n"
+        "popc.b32 t, v;\n"
+        "mad.lo.u32 %1, t, 2, %1;\n"
+        "}\n"
+        : "+r"(state), "+r"(wa)
+        : "r"(thr), "r"(ltMask), "r"(one)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 v, t, a, w;\n"
+        ".reg .b16 h;\n"
+        "setp.ge.u32 p, %0, %2;\n"
+        "mov.b32 w, %0;\n"
+        "shr.u32 t, %0, 16;\n"
+        "selp.b32 %0, t, %0, p;\n"
+        "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+        "and.b32 t, v, %3;\n"
+        "popc.b32 t, t;\n"
+        "mad.lo.u32 a, t, 2, %1;\n"
+        "cvt.u16.u32 h, w;\n"
+        "@p st.shared.u16 [a], h;\n"
+        "popc.b32 t, v;\n"
+        "mad.lo.u32 %1, t, 2, %1;\n"
+        "}\n"
+        : "+r"(state), "+r"(wa)
+        : "r"(thr), "r"(ltMask)
+        : "memory");
+  }
 }
 
 // Table entry -> the values a row needs.  Two formats (common.cuh), chosen per call by what the
@@ -540,12 +569,14 @@ __device__ __forceinline__ void emitWords(uint32_t& state, uint32_t thr, uint32_
 // Everything here is independent of the coder state, so it runs ahead of the serial chain.
 struct EncRegs {
   uint32_t tabAddr, ltMask, thrNegScale;  // thrNegScale = -(2^(31 - pb)), packed format only
+  uint32_t one;                           // 1, but not a compile-time constant (see emitWords)
 };
 __device__ __forceinline__ EncRegs makeEncRegs(uint32_t tabAddr, int pb) {
   EncRegs r;
   r.tabAddr = tabAddr;
   r.ltMask = laneMaskLt();
   r.thrNegScale = 0u - (1u << (31 - pb));
+  r.one = 1u + ((uint32_t)pb >> 31);  // pb is a kernel argument
   return r;
 }
 
@@ -554,14 +585,14 @@ struct EncSym;
 template <>
 struct EncSym<true> {
   static constexpr uint32_t kStride = 16;
-  uint32_t thr, magic, kmpShift, cdf;
+  uint32_t thr, magic, kmpv, cdfShift;
   __device__ __forceinline__ void load(uint32_t addr, const EncRegs&) {
     // not volatile: the table is read-only while a block is encoded, so the scheduler may hoist it
-    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(thr), "=r"(magic), "=r"(kmpShift), "=r"(cdf) : "r"(addr));
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(thr), "=r"(magic), "=r"(kmpv), "=r"(cdfShift) : "r"(addr));
   }
-  __device__ __forceinline__ uint32_t shiftReg() const { return kmpShift; }               // low 5 bits count
-  __device__ __forceinline__ uint32_t kmp() const { return kmpShift >> 8; }
-  __device__ __forceinline__ uint32_t plusCdf(uint32_t x) const { return x + cdf; }
+  __device__ __forceinline__ uint32_t shiftReg() const { return cdfShift; }  // low 5 bits count
+  __device__ __forceinline__ uint32_t kmp() const { return kmpv; }
+  __device__ __forceinline__ uint32_t plusCdf(uint32_t x) const { return x + (cdfShift >> 5); }  // one LEA.HI
 };
 template <>
 struct EncSym<false> {
@@ -587,7 +618,7 @@ template <bool WIDE>
 __device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t sym, const EncRegs& rc, uint32_t& wa) {
   EncSym<WIDE> e;
   e.load(rc.tabAddr + sym * EncSym<WIDE>::kStride, rc);
-  emitWords(state, e.thr, wa, rc.ltMask);
+  emitWords<!WIDE>(state, e.thr, wa, rc.ltMask, rc.one);
   encodeUpdate(state, e);
 }
 
@@ -597,7 +628,7 @@ __device__ __forceinline__ void encodeStepPartial(bool valid, uint32_t& state, u
   EncSym<WIDE> e;
   e.load(rc.tabAddr + sym * EncSym<WIDE>::kStride, rc);
   // invalid lanes never emit: compare against an unreachable threshold
-  emitWords(state, valid ? e.thr : 0xffffffffu, wa, rc.ltMask);
+  emitWords<!WIDE>(state, valid ? e.thr : 0xffffffffu, wa, rc.ltMask, rc.one);
   uint32_t next = state;
   encodeUpdate(next, e);
   state = valid ? next : state;
@@ -632,7 +663,7 @@ __device__ __forceinline__ void encodeGroup(uint32_t& state, uint32_t ringLane, 
   for (int j = 0; j < U; ++j) {
     const EncSym<WIDE> cur = e[j % kDepth];
     if (j + kDepth < U) e[j % kDepth].load(addr[j + kDepth], rc);
-    emitWords(state, cur.thr, wa, rc.ltMask);
+    emitWords<!WIDE>(state, cur.thr, wa, rc.ltMask, rc.one);
     encodeUpdate(state, cur);
   }
 }
