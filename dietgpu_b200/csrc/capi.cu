@@ -3,6 +3,7 @@
 // size; ans/BatchProvider.cuh) onto one internal member list, so every kernel
 // sees a single descriptor table uploaded in one copy.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -78,7 +79,11 @@ int autoParts(int kind, uint32_t n, uint64_t totalBytes, bool decode) {
   return (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)p, n));
 }
 
+// kernels launched by this library since load (every codec launch site calls timerBegin first)
+static std::atomic<int> gLaunches{0};
+
 void timerBegin(int slot, cudaStream_t stream) {
+  gLaunches.fetch_add(1, std::memory_order_relaxed);
   if (!options().timing) return;
   TimedLaunch t{slot, takeEvent(), takeEvent()};
   cudaEventRecord(t.a, stream);
@@ -358,6 +363,11 @@ int dgb_kernel_times(float* ms, int* counts, int nslots) {
 }
 
 int dgb_get_option(const char* name, int* value) {
+  // read-only counter: hot-path kernels launched so far (stats, encode, plan, decode)
+  if (name && value && !std::strcmp(name, "launches")) {
+    *value = dgb::gLaunches.load(std::memory_order_relaxed);
+    return DGB_OK;
+  }
   int* s = optionSlot(name);
   if (!s || !value) return DGB_ERR_INVALID_ARG;
   *value = *s;

@@ -10,3 +10,4 @@ $NCU -k regex:decodeKernel -s 2 -c 1 -o gpurun_out/final_decode_c3 -f python too
 $NCU -k regex:encodeKernelFast -s 2 -c 1 -o gpurun_out/final_encode_c3 -f python tools/prof_one.py c3 3 parts=1 > /dev/null 2>&1
 $NCU -k regex:statsFloatKernel -s 2 -c 1 -o gpurun_out/final_stats_c3 -f python tools/prof_one.py c3 3 parts=1 > /dev/null 2>&1
 ls -la gpurun_out/final_*
+python tools/walltime.py c3 "decode_slot_words=2048" "decode_slot_words=1536" "decode_slot_words=0" > gpurun_out/final_walltime.txt 2>&1; tail -3 gpurun_out/final_walltime.txt
