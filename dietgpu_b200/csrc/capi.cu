@@ -35,18 +35,28 @@ cudaEvent_t takeEvent() {
 thread_local TimedLaunch tlsOpen[kNumSlots];
 }  // namespace
 
+// One pool per (host thread, device): the fork/join events of a call must not be shared with a call
+// that another thread, or the same thread on another device, makes at the same time.
 int streamPool(StreamPool** out) {
-  static StreamPool pool;
-  static bool ready = false;
-  if (!ready) {
+  constexpr int kMaxDevices = 64;
+  struct Slot {
+    StreamPool pool;
+    bool ready = false;
+  };
+  static thread_local Slot slots[kMaxDevices];
+  int dev = 0;
+  DGB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return DGB_ERR_INVALID_ARG;
+  Slot& sl = slots[dev];
+  if (!sl.ready) {
     for (int i = 0; i < kMaxParts; ++i) {
-      DGB_CUDA_TRY(cudaStreamCreateWithFlags(&pool.s[i], cudaStreamNonBlocking));
-      DGB_CUDA_TRY(cudaEventCreateWithFlags(&pool.done[i], cudaEventDisableTiming));
+      DGB_CUDA_TRY(cudaStreamCreateWithFlags(&sl.pool.s[i], cudaStreamNonBlocking));
+      DGB_CUDA_TRY(cudaEventCreateWithFlags(&sl.pool.done[i], cudaEventDisableTiming));
     }
-    DGB_CUDA_TRY(cudaEventCreateWithFlags(&pool.start, cudaEventDisableTiming));
-    ready = true;
+    DGB_CUDA_TRY(cudaEventCreateWithFlags(&sl.pool.start, cudaEventDisableTiming));
+    sl.ready = true;
   }
-  *out = &pool;
+  *out = &sl.pool;
   return DGB_OK;
 }
 

@@ -617,14 +617,16 @@ DecodePlan planDecodeScratch(uint32_t n) {
 }
 
 int smCountD() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
+  // per device (a process may drive several); racing first calls write the same value
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = v > 0 ? v : 148;
   }
-  return cached;
+  return cached[dev];
 }
 
 template <int KIND, int PB, int WARPS, bool STAGE, bool LUT64>
@@ -644,14 +646,19 @@ int launchDecode(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t par
   size_t smemBytes = (2 * kNumSymbols + 64) * 4 + ((WARPS + 1) & ~1) * 8 +
                      (size_t)WARPS * kRingSlots * RowWriter<KIND>::kRingSlotBytes;
   if (STAGE) smemBytes += (size_t)WARPS * (128u + slotWords * 2u);
-  static int perSm = 0;  // per instantiation; one device per process (one rank per GPU)
-  static size_t perSmKey = 0;
-  if (perSm == 0 || perSmKey != smemBytes) {
+  // per instantiation and host thread; re-done when the thread's current device changes (function
+  // attributes are per device)
+  static thread_local int perSm = 0;
+  static thread_local size_t perSmKey = 0;
+  int devOrdinal = 0;
+  DGB_CUDA_TRY(cudaGetDevice(&devOrdinal));
+  const size_t occKey = smemBytes | ((size_t)(devOrdinal + 1) << 40);
+  if (perSm == 0 || perSmKey != occKey) {
     DGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int occ = 0;
     DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smemBytes));
     perSm = std::max(occ, 1);
-    perSmKey = smemBytes;
+    perSmKey = occKey;
   }
   // one resident wave; every warp gets the same number of blocks (rounds) when the batch is
   // large, so no warp idles at the CTA barrier waiting for a neighbour's extra block

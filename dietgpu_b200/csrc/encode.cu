@@ -1047,14 +1047,16 @@ ScratchPlan planScratch(int kind, uint32_t n, uint32_t maxSize, uint32_t totalTi
 }
 
 int smCount() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
+  // per device (a process may drive several); racing first calls write the same value
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = v > 0 ? v : 148;
   }
-  return cached;
+  return cached[dev];
 }
 
 uint32_t ticketsFor(uint32_t size) { return divUp(size, kBlockBytes); }
@@ -1146,20 +1148,24 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   slotWords = std::max<uint32_t>(roundUp(slotWords, 8u), kEncGroupRows * 32u + 264u);
   slotWords = std::min(slotWords, maxBlockWords(pb));
   const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb) : encFastWarpSmem(slotWords));
-  static bool configured = false;
-  if (!configured) {
+  // launch attributes and occupancy: cached per host thread, re-done when the kernel variant, its
+  // shared-memory size or the thread's current device changes (function attributes are per device)
+  int devOrdinal = 0;
+  DGB_CUDA_TRY(cudaGetDevice(&devOrdinal));
+  static thread_local int configuredDev = -1;
+  if (configuredDev != devOrdinal) {
     DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    configured = true;
+    configuredDev = devOrdinal;
   }
-  static size_t occKeySmem = 0;
-  static uint32_t occKeyW = 0;
-  static int occKeyCanon = -1;
-  static int perSm = 1;
+  static thread_local size_t occKeySmem = 0;
+  static thread_local uint32_t occKeyW = 0;
+  static thread_local int occKeyVariant = -1, occKeyDev = -1;
+  static thread_local int perSm = 1;
   // 0: canonical kernel (packed table), 1: fast kernel + packed table, 2: fast kernel + wide table
   const int variant = canonical ? 0 : (wideTable ? 2 : 1);
-  if (occKeySmem != smemBytes || occKeyW != W || occKeyCanon != variant) {
+  if (occKeySmem != smemBytes || occKeyW != W || occKeyVariant != variant || occKeyDev != devOrdinal) {
     int occ = 0;
     if (variant == 0) {
       DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel, (int)(W * 32), smemBytes));
@@ -1171,7 +1177,8 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     perSm = std::max(occ, 1);
     occKeySmem = smemBytes;
     occKeyW = W;
-    occKeyCanon = variant;
+    occKeyVariant = variant;
+    occKeyDev = devOrdinal;
   }
   const uint64_t resident = (uint64_t)perSm * sms;
   const uint32_t spillWarpsPerPart = kMaxSpillWarps / (uint32_t)parts;

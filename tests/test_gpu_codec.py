@@ -411,6 +411,37 @@ def test_sub_batch_streams():
         capi.set_option("parts", 0)
 
 
+def test_two_host_threads_with_sub_batches():
+    # two host threads, each on its own CUDA stream, both forcing sub-batch streams: the internal
+    # fork/join streams and events are per thread, so the calls must not disturb each other
+    import threading
+
+    from dietgpu_b200 import capi
+
+    errs = []
+
+    def worker(seed):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for it in range(6):
+                    float_roundtrip("bf16", [normal_words(60000 + 1000 * i, "bf16", seed + i) for i in range(9)], 10,
+                                    checksum=True)
+                    ans_roundtrip([exp_bytes(30000 + 4097 * i, 20, seed + i) for i in range(7)], 10)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    try:
+        capi.set_option("parts", 3)
+        th = [threading.Thread(target=worker, args=(100 * k,)) for k in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+    finally:
+        capi.set_option("parts", 0)
+    assert not errs, errs
+
+
 def test_encoder_table_formats():
     # the encoder symbol table has a 16-byte and an 8-byte entry format (chosen by data kind);
     # force each one on every kind, all precisions, incl. pdf == 1 symbols and a single-symbol input
