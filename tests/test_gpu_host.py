@@ -63,3 +63,19 @@ def test_host_float_roundtrip(kind, tdt):
     bad[2][0:4] = 0
     with pytest.raises(RuntimeError):
         hc.decompress(bad, host_out)
+
+
+@pytest.mark.parametrize("dt,n", [(torch.bfloat16, 300001), (torch.float32, 70000), (torch.uint8, 123457),
+                                  (torch.int32, 50000), (torch.float16, 5)])
+def test_all_gather_compressed_one_rank(dt, n):
+    # single process (no process group): compress -> pack -> unpack -> decompress must be the identity
+    from dietgpu_b200.collectives import all_gather_compressed
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    if dt.is_floating_point:
+        t = torch.randn(n, generator=g, device="cuda", dtype=torch.float32).to(dt)
+    else:
+        t = torch.randint(0, 100, (n,), generator=g, device="cuda", dtype=torch.int32).to(dt)
+    out = all_gather_compressed(t, members=5)
+    assert out.dtype == dt and out.numel() == n
+    assert torch.equal(out.view(torch.uint8), t.view(torch.uint8))

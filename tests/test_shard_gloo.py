@@ -7,6 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from dietgpu_b200.collectives import exchange_archives, pack_offsets
 from dietgpu_b200.shard import gather_sizes, shard_members, shard_range
 
 
@@ -52,3 +53,54 @@ def test_gather_sizes_world2(n):
         assert p.exitcode == 0
     want = [1000 + 16 * i for i in range(n)]
     assert res[0] == want and res[1] == want
+
+
+def test_pack_offsets():
+    offs, total = pack_offsets([0, 1, 16, 17, 4096])
+    assert offs == [0, 0, 16, 32, 64] and total == 64 + 4096
+
+
+def _archive(rank, i, size):
+    g = torch.Generator().manual_seed(1000 * rank + i)
+    return torch.randint(0, 256, (size,), dtype=torch.uint8, generator=g)
+
+
+def _exchange_worker(rank, world, port, sizes, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rows = [_archive(rank, i, s) for i, s in enumerate(sizes[rank])]
+        got = exchange_archives(rows)
+        ok = len(got) == world
+        for w in range(world):
+            ok = ok and len(got[w]) == len(sizes[w])
+            for i, s in enumerate(sizes[w]):
+                ok = ok and got[w][i].numel() == s and torch.equal(got[w][i], _archive(w, i, s))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sizes", [[[160, 48, 4112], [16, 70000, 32]], [[32], [1616]]])
+def test_exchange_archives_world2(sizes):
+    # variable-size archives, different totals per rank: sizes all-gather + padded payload all-gather
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 200) + len(sizes[0])
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, sizes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
+
+
+def test_exchange_archives_single_process():
+    rows = [_archive(0, i, s) for i, s in enumerate([16, 4096])]
+    got = exchange_archives(rows)
+    assert len(got) == 1 and all(torch.equal(a, b) for a, b in zip(got[0], rows))
+    with pytest.raises(ValueError):
+        exchange_archives([])
