@@ -9,16 +9,20 @@
 //                        histogram, bit-identical to the reference
 //                        (ans/GpuANSStatistics.cuh:178-367), writes the pdf
 //                        into the archive and the encoder table to scratch.
-//   K2  encodeKernel     persistent CTAs take ORDERED tickets of W consecutive
-//                        4 KiB blocks of one member; each warp runs the 32-lane
-//                        interleaved rANS state machine of its block
-//                        (ans/GpuANSEncode.cuh:49-211) into a shared-memory
-//                        staging slot; a decoupled look-back over the tickets
-//                        of the member gives the packed offset, so the words
-//                        go from shared memory straight to their final place
-//                        (the reference's uncoalesced scratch, prefix-sum
-//                        kernels and coalesce kernel -- ans/GpuANSEncode.cuh:
-//                        515-672, ans/BatchPrefixSum.cuh -- do not exist here).
+//   K2  encodeKernelFast one resident wave of CTAs, each owning a contiguous range of 4 KiB
+//                        blocks (one shared table load per member); each warp runs the
+//                        32-lane interleaved rANS state machine of its block
+//                        (ans/GpuANSEncode.cuh:49-211) into a shared-memory staging slot
+//                        and takes its place in the archive's data section with one 64-bit
+//                        atomic, so the words go from shared memory straight to their final
+//                        place (the reference's uncoalesced scratch, prefix-sum kernels and
+//                        coalesce kernel -- ans/GpuANSEncode.cuh:515-672,
+//                        ans/BatchPrefixSum.cuh -- do not exist here).  Streams land in
+//                        completion order, which the format allows (the decoder follows
+//                        blockWords[k].y).  Option encode_canonical selects encodeKernel:
+//                        ordered per-warp tickets + a decoupled look-back, block order,
+//                        byte-identical to the reference, slower.
+//   Large batches are cut by member into sub-batches on internal streams (capi.cu autoParts).
 //
 // The archive produced is field-for-field the reference's (A.4 of SURVEY.md);
 // bits the reference leaves undefined are zero.
