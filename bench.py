@@ -46,9 +46,11 @@ WORKLOADS = {
     # name: (kind, batch, elems per member, description)
     "c3": ("bf16", 64, 2 * MIB, "64 x 2Mi bf16 N(0,1) = 256 MiB, prec 10 (BASELINE configs[2])"),
     "c2": ("bytes", 64, 4 * MIB, "64 x 4MiB Zipf(s=1) bytes = 256 MiB, prec 10 (BASELINE configs[1])"),
+    "c2p11": ("bytes", 64, 4 * MIB, "64 x 4MiB Zipf(s=1) bytes = 256 MiB, prec 11 (BASELINE configs[1])"),
     "c4": ("f16", 256, 512 * 1024, "256 x 512Ki fp16 ReLU(N(0,1)) = 256 MiB, prec 10 (BASELINE configs[3])"),
     "c3x1": ("bf16", 1, 128 * MIB, "1 x 128Mi bf16 N(0,1) = 256 MiB, batch 1, prec 10"),
 }
+PROB_BITS = {"c2p11": 11}  # every other workload codes at the reference's default precision, 10
 
 
 def load_peaks():
@@ -138,9 +140,9 @@ class OursCodec:
     handling.  `api_*` go through the public operator mirror (dietgpu_b200.ops) for the e2e leg."""
     name = "ours"
 
-    def __init__(self, torch, kind, ts):
+    def __init__(self, torch, kind, ts, pb=10):
         import dietgpu_b200 as dg
-        self.dg, self.torch, self.kind, self.ts = dg, torch, kind, ts
+        self.dg, self.torch, self.kind, self.ts, self.pb = dg, torch, kind, ts, pb
         self.as_float = kind != "bytes"
         n = self.n = len(ts)
         dev = ts[0].device
@@ -171,10 +173,10 @@ class OursCodec:
     def encode(self):
         L = self.L
         if self.as_float:
-            rc = L.dgb_float_compress_pointer(self.tp, self.tb, self.ft, 10, 0, self.n, self.in_ptrs, self.in_sizes,
+            rc = L.dgb_float_compress_pointer(self.tp, self.tb, self.ft, self.pb, 0, self.n, self.in_ptrs, self.in_sizes,
                                               self.row_ptrs, self.sizes.data_ptr(), self._stream())
         else:
-            rc = L.dgb_ans_encode_pointer(self.tp, self.tb, 10, 0, self.n, self.in_ptrs, self.in_sizes, None,
+            rc = L.dgb_ans_encode_pointer(self.tp, self.tb, self.pb, 0, self.n, self.in_ptrs, self.in_sizes, None,
                                           self.row_ptrs, self.sizes.data_ptr(), self._stream())
         assert rc == 0, rc
 
@@ -186,28 +188,26 @@ class OursCodec:
     def decode(self):
         L = self.L
         if self.as_float:
-            rc = L.dgb_float_decompress_pointer(self.tp, self.tb, self.ft, 10, 0, self.n, self.row_ptrs, self.out_ptrs,
+            rc = L.dgb_float_decompress_pointer(self.tp, self.tb, self.ft, self.pb, 0, self.n, self.row_ptrs, self.out_ptrs,
                                                 self.in_sizes, None, None, None, self._stream())
         else:
-            rc = L.dgb_ans_decode_pointer(self.tp, self.tb, 10, 0, self.n, self.row_ptrs, self.out_ptrs, self.in_sizes,
+            rc = L.dgb_ans_decode_pointer(self.tp, self.tb, self.pb, 0, self.n, self.row_ptrs, self.out_ptrs, self.in_sizes,
                                           None, None, None, self._stream())
         assert rc == 0, rc
 
     def api_encode(self):
-        self.dg.compress_data(self.as_float, self.ts, False, self.temp, self.comp, self.sizes)
+        self.dg.compress_data(self.as_float, self.ts, False, self.temp, self.comp, self.sizes, prob_bits=self.pb)
 
     def api_decode(self):
-        self.dg.decompress_data(self.as_float, self.rows, self.outs, False, self.temp)
-
-    launches_per_step = 4  # stats + encode + plan + decode
+        self.dg.decompress_data(self.as_float, self.rows, self.outs, False, self.temp, prob_bits=self.pb)
 
 
 class RefGpuCodec:
     name = "reference"
 
-    def __init__(self, torch, kind, ts):
+    def __init__(self, torch, kind, ts, pb=10):
         from oracle import ref_lib
-        self.torch, self.kind, self.ts = torch, kind, ts
+        self.torch, self.kind, self.ts, self.pb = torch, kind, ts, pb
         self.as_float = kind != "bytes"
         self.ft = {"bf16": 2, "f16": 1}.get(kind, 0)
         n = len(ts)
@@ -242,10 +242,10 @@ class RefGpuCodec:
     def encode(self):
         self._prep()
         if self.as_float:
-            self.RL.ref_float_compress(self.tptr, self.tbytes, self.ft, 10, 0, self.n, self.a_in, self.a_sz, self.a_rows,
+            self.RL.ref_float_compress(self.tptr, self.tbytes, self.ft, self.pb, 0, self.n, self.a_in, self.a_sz, self.a_rows,
                                        self.sizes.data_ptr(), self._stream())
         else:
-            self.RL.ref_ans_encode_pointer(self.tptr, self.tbytes, 10, 0, self.n, self.a_in, self.a_sz, self.a_rows,
+            self.RL.ref_ans_encode_pointer(self.tptr, self.tbytes, self.pb, 0, self.n, self.a_in, self.a_sz, self.a_rows,
                                            self.sizes.data_ptr(), self._stream())
 
     def bind_rows(self):
@@ -256,10 +256,10 @@ class RefGpuCodec:
     def decode(self):
         self._prep()
         if self.as_float:
-            self.RL.ref_float_decompress(self.tptr, self.tbytes, self.ft, 10, 0, 1, self.n, self.a_rows, self.a_out,
+            self.RL.ref_float_decompress(self.tptr, self.tbytes, self.ft, self.pb, 0, 1, self.n, self.a_rows, self.a_out,
                                          self.a_sz, None, None, self._stream())
         else:
-            self.RL.ref_ans_decode_pointer(self.tptr, self.tbytes, 10, 0, self.n, self.a_rows, self.a_out, self.a_sz,
+            self.RL.ref_ans_decode_pointer(self.tptr, self.tbytes, self.pb, 0, self.n, self.a_rows, self.a_out, self.a_sz,
                                            None, None, self._stream())
 
     def api_encode(self):
@@ -326,7 +326,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--all-workloads", action="store_true", help="add encode/decode GB/s of every workload under 'detail'")
+    ap.add_argument("--all-workloads", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--no-detail", action="store_true", help="skip the short runs of the other BASELINE workloads")
     args = ap.parse_args()
 
     import torch
@@ -362,8 +363,9 @@ def main():
 
     def run_workload(name, steps, warmup, full):
         kind, batch, per, desc = WORKLOADS[name]
+        pb = PROB_BITS.get(name, 10)
         ts = make_batch(torch, kind, batch, per, 1234 + 1000 * rank, dev)
-        codec = RefGpuCodec(torch, kind, ts) if use_ref_gpu else OursCodec(torch, kind, ts)
+        codec = RefGpuCodec(torch, kind, ts, pb) if use_ref_gpu else OursCodec(torch, kind, ts, pb)
         ubytes = sum(t.numel() * t.element_size() for t in ts)
         stream = torch.cuda.current_stream()
 
@@ -421,7 +423,7 @@ def main():
             "t_tot": t_tot, "t_enc": t_enc, "t_dec": t_dec,
             "encode_gbs": world * ubytes * steps / t_enc / 1e9, "decode_gbs": world * ubytes * steps / t_dec / 1e9,
             "value": world * 2 * ubytes * steps / t_tot / 1e9, "clocks": clocks, "cbytes_all": cbytes_all,
-            "launches": launches,
+            "launches": launches, "prob_bits": pb,
         }
         if not full:
             return res
@@ -496,7 +498,7 @@ def main():
         # ours: the host-buffer front end (dietgpu_b200.HostCodec), same bytes over the link, but upload /
         # codec / download of different member groups overlap on three streams
         import dietgpu_b200 as dg
-        hc = dg.HostCodec(kind != "bytes", pin_in, device=dev, groups=8)
+        hc = dg.HostCodec(kind != "bytes", pin_in, device=dev, groups=8, prob_bits=pb)
         pin_comp2 = torch.empty((len(ts), hc.max_archive_bytes()), dtype=torch.uint8, pin_memory=True)
 
         def host_step():
@@ -528,11 +530,13 @@ def main():
         #   floats: stats  reads 2F(words) writes the stored plane(s) + header, decode reads C_f writes 2F
         #   encode reads the F comp bytes and writes the ANS archive
         nfl = ubytes // (2 if kind in ("bf16", "f16") else 1)
+        # the fused encoder is ONE launch per call: its algorithmic bytes are the whole direction's, U + C
         if kind == "bytes":
-            alg = {"stats": ubytes, "encode": ubytes + cbytes, "decode": cbytes + ubytes}
+            alg = {"stats": ubytes, "encode": ubytes + cbytes, "decode": cbytes + ubytes, "encode_fused": ubytes + cbytes}
         else:
             ans_bytes = cbytes - (nfl + 16 * main_res["batch"])
-            alg = {"stats": ubytes + nfl, "encode": nfl + ans_bytes, "decode": cbytes + ubytes}
+            alg = {"stats": ubytes + nfl, "encode": nfl + ans_bytes, "decode": cbytes + ubytes,
+                   "encode_fused": ubytes + cbytes}
         for k, v in main_res["kernels"].items():
             if k in alg:
                 a = alg[k] / (v["ms_avg"] / 1e3) / 1e9
@@ -560,12 +564,23 @@ def main():
             a = (ubytes + cbytes) * steps / t / 1e9
             roofline_all[d] = {"achieved": round(a, 1), "frac": round(a / peak, 4), "unit": "GB/s"}
 
+    # every BASELINE config in the same line (north_star: bytes prec 10/11, fp16, bf16, at every N):
+    # short runs of the other workloads, same timing rules, every rank takes part
     detail = {}
-    if args.all_workloads:
+    if not args.no_detail:
+        dsteps = max(5, args.steps // 5)
         for w in sorted(WORKLOADS):
-            r = main_res if w == args.workload else run_workload(w, max(3, args.steps // 4), 3, False)
-            detail[w] = {"encode_gbs": round(r["encode_gbs"], 1), "decode_gbs": round(r["decode_gbs"], 1),
-                         "ratio": r["ratio"], "verified": r["verified"]}
+            if w == args.workload:
+                r, st = main_res, args.steps
+            else:
+                torch.cuda.empty_cache()
+                r, st = run_workload(w, dsteps, 3, False), dsteps
+            alg_dir = (r["ubytes"] + r["cbytes"]) * world  # U + C per direction
+            detail[w] = {"desc": r["desc"], "prob_bits": r["prob_bits"], "steps": st,
+                         "encode_gbs": round(r["encode_gbs"], 1), "decode_gbs": round(r["decode_gbs"], 1),
+                         "value": round(r["value"], 1), "ratio": r["ratio"], "verified": r["verified"],
+                         "encode_roofline_frac": round(alg_dir * st / r["t_enc"] / 1e9 / (peak * world), 4),
+                         "decode_roofline_frac": round(alg_dir * st / r["t_dec"] / 1e9 / (peak * world), 4)}
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -582,7 +597,7 @@ def main():
             "dtype": "u32 integer state machine on u8 symbols", "data": "synthetic",
             "config": {"workload": main_res["desc"], "batch": main_res["batch"],
                        "uncompressed_bytes_per_gpu": ubytes, "compressed_bytes_per_gpu": cbytes,
-                       "ratio": main_res["ratio"], "prob_bits": 10, "checksum": False,
+                       "ratio": main_res["ratio"], "prob_bits": main_res["prob_bits"], "checksum": False,
                        "l2": "inputs (256 MiB) + archives (~172 MiB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"batch shard x{world}, no data-path collective"},
             "encode_gbs": round(main_res["encode_gbs"], 2), "decode_gbs": round(main_res["decode_gbs"], 2),

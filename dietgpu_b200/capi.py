@@ -127,7 +127,7 @@ def u32_array(vals):
     return (C.c_uint32 * len(vals))(*[int(v) for v in vals])
 
 
-KERNEL_SLOTS = ["stats", "encode", "plan", "decode", "checksum"]
+KERNEL_SLOTS = ["stats", "encode", "plan", "decode", "checksum", "encode_fused"]
 
 
 def kernel_times():

@@ -144,14 +144,21 @@ int dgb_last_cuda_error(void) { return (int)tlsLastCuda; }
 
 uint32_t dgb_ans_max_compressed_size(uint32_t bytes) {
   // ans/GpuANSEncode.cu:13-25 (the header overhead is charged for a constant 4096 blocks)
+  // The reference CHECKs rawSize <= INT32_MAX (process abort); this ABI returns 0 = "too large"
+  // instead of a wrapped value a caller would size its output buffer from.
   uint64_t raw = ansOverhead(kBlockBytes);
   raw += (uint64_t)roundUp(kBlockBytes + kBlockBytes / 4u, 16u) * divUp(bytes, kBlockBytes);
-  return (uint32_t)roundUp64(raw, 16);
+  raw = roundUp64(raw, 16);
+  return raw <= 0x7fffffffull ? (uint32_t)raw : 0u;
 }
 
 uint32_t dgb_float_max_compressed_size(int ft, uint32_t n) {
   if (!validFloatType(ft)) return 0;
-  return kFloatHeaderBytes + dgb_ans_max_compressed_size(n) + floatNonCompBytes(ft, n);
+  const uint32_t ans = dgb_ans_max_compressed_size(n);
+  if (ans == 0u) return 0u;  // too large (see above)
+  const uint64_t non = ft == DGB_FLOAT32 ? 2ull * roundUp64(n, 8) + roundUp64(n, 16) : roundUp64(n, 16);
+  const uint64_t total = (uint64_t)kFloatHeaderBytes + ans + non;
+  return total <= 0xffffffffull ? (uint32_t)total : 0u;
 }
 
 size_t dgb_ans_encode_temp_bytes(uint32_t n, uint32_t maxBytes) {
@@ -333,16 +340,17 @@ int dgb_float_get_compressed_info(void* temp, size_t tempBytes, const void* cons
 static int* optionSlot(const char* name) {
   Options& o = options();
   if (!name) return nullptr;
-  if (!std::strcmp(name, "decode_stage")) return &o.decode_stage;
-  if (!std::strcmp(name, "decode_warps")) return &o.decode_warps;
-  if (!std::strcmp(name, "decode_lut64")) return &o.decode_lut64;
+  if (!std::strcmp(name, "decode_fused")) return &o.decode_fused;
+  if (!std::strcmp(name, "decode_chunk_blocks")) return &o.decode_chunk_blocks;
   if (!std::strcmp(name, "decode_slot_words")) return &o.decode_slot_words;
   if (!std::strcmp(name, "encode_warps")) return &o.encode_warps;
   if (!std::strcmp(name, "encode_canonical")) return &o.encode_canonical;
+  if (!std::strcmp(name, "encode_fused")) return &o.encode_fused;
+  if (!std::strcmp(name, "fused_stats_every")) return &o.fused_stats_every;
+  if (!std::strcmp(name, "fused_chunk_blocks")) return &o.fused_chunk_blocks;
   if (!std::strcmp(name, "encode_wide_table")) return &o.encode_wide_table;
   if (!std::strcmp(name, "encode_slot_words")) return &o.encode_slot_words;
   if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
-  if (!std::strcmp(name, "hist_mode")) return &o.hist_mode;
   if (!std::strcmp(name, "hist_ctas_per_sm")) return &o.hist_ctas_per_sm;
   if (!std::strcmp(name, "timing")) return &o.timing;
   if (!std::strcmp(name, "parts")) return &o.parts;

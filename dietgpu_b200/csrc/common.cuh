@@ -71,17 +71,18 @@ struct __align__(16) EncEntryWide {
 
 // ---- tuning options (dgb_set_option) ---------------------------------------
 struct Options {
-  int decode_stage = 1;      // 1: stream staged into smem with cp.async.bulk (TMA); 0: direct LDG
-  int decode_warps = 8;      // warps per decode CTA (4 or 8)
-  int decode_lut64 = 0;      // 1: 8-byte decode LUT entries (fewer ALU ops, more smem)
+  int decode_fused = 1;      // 1: one persistent launch with member-affine chunk claiming; 0: plan + decode kernels
+  int decode_chunk_blocks = 16;  // single-launch decoder: 4 KiB blocks per claimed chunk
   int decode_slot_words = 0; // TMA staging slot per warp in u16 words; 0 = auto
   int encode_warps = 8;      // warps per encode CTA (each warp is an independent worker)
   int encode_slot_words = 0; // staging slot of the fast encoder in u16 words; 0 = auto
   int encode_canonical = 0;  // 1: streams packed in block order (byte-identical archives, slower)
+  int encode_fused = 1;      // 1: one persistent launch (statistics items + encode chunks), 0: two kernels
+  int fused_stats_every = 4; // fused launch: one CTA in this many prefers statistics items (0: none does)
+  int fused_chunk_blocks = 16;  // fused launch: 4 KiB blocks per encode chunk
   int encode_wide_table = -1;  // encoder table entries: 1 = 16 B, 0 = 8 B, -1 = by data kind (bf16/fp32 wide)
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_ctas_per_sm = 32; // stats grid = this many CTAs per SM (each CTA loops over slabs)
-  int hist_mode = 0;         // 0: per-warp smem atomics; 1: per-lane private byte counters
   int parts = 0;             // sub-batches run on internal streams (0 = auto, 1 = off, max 4)
   int timing = 0;            // 1: bracket every kernel launch with CUDA events (bench.py roofline pass)
 };
@@ -110,7 +111,7 @@ void setLastCudaError(cudaError_t e);
 
 // Per-kernel timing (options().timing): slots are stable indices reported by
 // dgb_kernel_times().  No-ops when timing is off.
-enum TimerSlot : int { kSlotStats = 0, kSlotEncode = 1, kSlotPlan = 2, kSlotDecode = 3, kSlotChecksum = 4, kNumSlots = 5 };
+enum TimerSlot : int { kSlotStats = 0, kSlotEncode = 1, kSlotPlan = 2, kSlotDecode = 3, kSlotChecksum = 4, kSlotFused = 5, kNumSlots = 6 };
 // Internal helper streams: a large batch is cut into up to kMaxParts contiguous sub-batches whose
 // kernels run on separate streams (forked from / joined to the caller's stream with events), so the
 // HBM-bound and the issue-bound kernels of different sub-batches overlap and launch gaps hide.

@@ -38,7 +38,9 @@ namespace dgb {
 namespace {
 
 struct DecodeScratch {
-  MemberDesc* members;   // [n]; planKernel fills work0 = first flat block
+  MemberDesc* members;   // [n]; two-kernel path: planKernel fills work0 = first flat block;
+                         //      single-launch path: work0 = the member's chunk count (host, from capacity)
+  uint32_t* next;        // [n] single-launch path: next unclaimed chunk of the member (zeroed)
   uint32_t* totals;      // [0] = total blocks, [1] = unused
   uint32_t* checksum;    // [n] checksum of decoded output (use_checksum only; zeroed)
   uint32_t* archiveChecksum;  // [n]
@@ -317,7 +319,9 @@ struct Lut<PB, false> {
   }
   static __device__ __forceinline__ uint32_t step(uint32_t& state, const Entry* __restrict__ lut) {
     const uint32_t e = lut[state & ((1u << PB) - 1u)];
-    state = (e >> 20) * (state >> PB) + ((e >> 8) & 0xfffu);
+    // e >> 8 = pdf * 4096 + (s - cdf): the multiple of pdf is taken back out of the quotient, so the
+    // (s - cdf) field needs no mask (all arithmetic mod 2^32); the -4096 folds into the shift (LEA.HI)
+    state = (e >> 20) * ((state >> PB) - 4096u) + (e >> 8);
     return e;
   }
 };
@@ -583,6 +587,170 @@ decodeKernel(DecodeScratch sc, uint32_t m0, uint32_t m1, uint32_t part, uint32_t
   }
 }
 
+// ---------------------------------------------------------------------------
+// Single-launch decoder (default).  One persistent grid, no plan kernel, no sub-batches: the host
+// knows every member's capacity, so it cuts each member into chunks of `chunkBlocks` 4 KiB blocks
+// (work0 = chunk count, at least one so that every header is visited) and zeroes one claim counter
+// per member.  A CTA starts at its home member, claims chunks of that member with one atomic each
+// (the next claim is issued before the current chunk is decoded, so its latency hides), and moves
+// on to the next member that still has unclaimed chunks when its own runs out: the decode LUT is
+// rebuilt only on a member switch, and all CTAs finish within one chunk of each other (the static
+// split of the two-kernel path left SMs idle for ~15 % of the kernel, ncu r01).  The CTA that
+// claims chunk 0 of a member validates its header(s) and reports outSuccess / outSize
+// (ans/GpuANSDecode.cuh:326-341 semantics); chunks past the archive's real block count, or of a
+// member that failed, are claimed and dropped.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kNoMember = 0xffffffffu;
+
+template <int KIND, int PB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, DGB_DECODE_WARPS_PER_SM / WARPS)
+decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t chunkBlocks, uint32_t slotWords,
+                  uint8_t* __restrict__ outSuccess, uint32_t* __restrict__ outSize, bool wantChecksum) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr uint32_t K = 1u << PB;
+  typedef typename Lut<PB, false>::Entry Entry;
+  __shared__ __align__(16) Entry lut[K];  // static: constant base address for the hot LDS
+  uint32_t* sPdf = reinterpret_cast<uint32_t*>(smem);
+  uint32_t* sCdf = sPdf + kNumSymbols;
+  uint32_t* sWarp = sCdf + kNumSymbols;           // 32 words
+  uint32_t* sMisc = sWarp + 32;                   // 32 words
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sMisc + 32);  // [WARPS]
+  uint8_t* sRing = reinterpret_cast<uint8_t*>(sBar + ((WARPS + 1) & ~1));  // [WARPS] stored-byte rings
+  constexpr uint32_t ringBytes = kRingSlots * RowWriter<KIND>::kRingSlotBytes;
+  uint8_t* sSlots = sRing + WARPS * ringBytes;
+  const uint32_t slotBytes = 128u + slotWords * 2u;  // lane states + stream
+
+  const uint32_t t = threadIdx.x, lane = t & 31u;
+  const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  uint8_t* mySlot = sSlots + (size_t)warp * slotBytes;
+  const uint32_t myBar = smemAddr(sBar + warp);
+  uint32_t phase = 0;
+  if (lane == 0) mbarInit(myBar, 1);
+  fenceBarrierInit();
+  __syncthreads();
+
+  // claim state: lives in warp 0 (uniform there), broadcast through sMisc
+  uint32_t cursor = (uint32_t)((uint64_t)blockIdx.x * n / gridDim.x);  // home member
+  uint32_t pending = kNoMember, pendingChunk = 0;  // a claim issued ahead of time (lane 0 of warp 0)
+  uint32_t lutMember = kNoMember;
+  bool memberOk = false;
+  uint32_t nb = 0;
+  ArchiveView av;
+  av.ok = false;
+  av.ans = nullptr; av.non = nullptr; av.floatWords = 0;
+
+  for (;;) {
+    if (warp == 0) {
+      uint32_t cm = kNoMember, cc = 0;
+      if (pending != kNoMember) {
+        // the claim made before the previous chunk was decoded
+        const uint32_t c = __shfl_sync(0xffffffffu, pendingChunk, 0);
+        if (c < __ldg(&sc.members[pending].work0)) { cm = pending; cc = c; }
+        else cursor = pending + 1 == n ? 0u : pending + 1;
+        pending = kNoMember;
+      }
+      uint32_t tries = 0;
+      while (cm == kNoMember && tries < n) {
+        // 32 members at a time: who still has unclaimed chunks?
+        uint32_t mm = cursor + lane;
+        if (mm >= n) mm -= n;
+        const bool inRange = tries + lane < n;
+        bool has = false;
+        if (inRange) has = *reinterpret_cast<volatile uint32_t*>(sc.next + mm) < __ldg(&sc.members[mm].work0);
+        const uint32_t mask = __ballot_sync(0xffffffffu, has);
+        if (mask == 0u) {
+          tries += 32u;
+          cursor = cursor + 32u >= n ? (cursor + 32u) % n : cursor + 32u;
+          continue;
+        }
+        const uint32_t first = (uint32_t)__ffs((int)mask) - 1u;
+        uint32_t cand = cursor + first;
+        if (cand >= n) cand -= n;
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(sc.next + cand, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c < __ldg(&sc.members[cand].work0)) { cm = cand; cc = c; cursor = cand; }
+        else { tries += first + 1u; cursor = cand + 1 == n ? 0u : cand + 1; }  // lost the race for its last chunk
+      }
+      if (cm != kNoMember) {
+        // next claim of the same member, in flight while this chunk is decoded
+        pending = cm;
+        if (lane == 0) pendingChunk = atomicAdd(sc.next + cm, 1u);
+      }
+      if (lane == 0) { sMisc[0] = cm; sMisc[1] = cc; }
+    }
+    __syncthreads();
+    const uint32_t m = sMisc[0], chunk = sMisc[1];
+    if (m == kNoMember) break;
+    const MemberDesc md = sc.members[m];
+    if (lutMember != m || chunk == 0u) {
+      // ---- member switch: header(s), validity, LUT ----
+      av = openArchive<KIND>(static_cast<const uint8_t*>(md.in));
+      bool ok = av.ok;
+      uint32_t need = 0, storedChecksum = 0;
+      nb = 0;
+      if (ok) {
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(av.ans));
+        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(av.ans) + 1);
+        nb = h0.y;
+        need = h0.z;  // uncompressed bytes == float words for float kinds
+        ok = h0.x == kAnsMagicVersion && (int)(h1.x & 0xfu) == PB && nb == divUp(need, kBlockBytes);
+        if (KIND != kKindBytes) ok = ok && need == av.floatWords;
+        storedChecksum = KIND == kKindBytes ? h1.y : __ldg(reinterpret_cast<const uint32_t*>(md.in) + 3);
+      }
+      // ans/GpuANSDecode.cuh:326-337: success iff capacity suffices; size reported regardless
+      memberOk = ok && md.size >= need;
+      if (chunk == 0u && t == 0) {
+        if (outSuccess) outSuccess[m] = memberOk ? 1 : 0;
+        if (outSize) outSize[m] = ok ? need : 0u;
+        if (wantChecksum) {
+          sc.archiveChecksum[m] = storedChecksum;
+          sc.sizes[m] = memberOk ? need : 0u;
+        }
+      }
+      if (memberOk && nb > 0 && lutMember != m) buildLut<PB, false, WARPS>(av.ans, lut, sPdf, sCdf, sWarp);
+      lutMember = memberOk && nb > 0 ? m : kNoMember;
+    }
+    if (memberOk) {
+      const uint8_t* pStates = av.ans + kAnsHeaderBytes + kAnsPdfBytes;
+      const uint2* pBlockWords = reinterpret_cast<const uint2*>(pStates + 128u * (size_t)nb);
+      const uint16_t* pData = reinterpret_cast<const uint16_t*>(
+          reinterpret_cast<const uint8_t*>(pBlockWords) + 8u * (size_t)roundUp(nb, 2u));
+      const bool canStage = (reinterpret_cast<uintptr_t>(av.ans) & 15u) == 0;
+      RowWriter<KIND> wr;
+      wr.setRing(smemAddr(sRing + warp * ringBytes), lane);
+      const uint32_t first = chunk * chunkBlocks;
+      const uint32_t last = min(nb, first + chunkBlocks);
+      for (uint32_t block = first + warp; block < last; block += WARPS) {
+        const uint2 bw = __ldg(pBlockWords + block);
+        const uint32_t blockLen = bw.x >> 16, words = bw.x & 0xffffu;
+        const uint16_t* stream = pData + bw.y;
+        wr.setBlock(av, md.out, block, lane);
+        // two call sites on purpose: each knows the address space of the stream
+        if (canStage && words <= slotWords && (bw.y & 7u) == 0u) {
+          const uint32_t streamBytes = roundUp(words, 8u) * 2u;
+          __syncwarp();
+          if (lane == 0) {
+            mbarExpectTx(myBar, 128u + streamBytes);
+            bulkLoad(smemAddr(mySlot), pStates + 128u * (size_t)block, 128u, myBar);
+            if (streamBytes) bulkLoad(smemAddr(mySlot + 128), stream, streamBytes, myBar);
+          }
+          mbarWait(myBar, phase);
+          phase ^= 1u;
+          const uint32_t state = reinterpret_cast<const uint32_t*>(mySlot)[lane];
+          SmemStream st{smemAddr(mySlot + 128) + 2u * words};
+          decodeBlockWarp<KIND, PB, false>(state, st, blockLen, lut, wr, lane);
+        } else {
+          const uint32_t state = __ldg(reinterpret_cast<const uint32_t*>(pStates) + block * 32u + lane);
+          GmemStream st{stream + words};
+          decodeBlockWarp<KIND, PB, false>(state, st, blockLen, lut, wr, lane);
+        }
+      }
+    }
+    __syncthreads();  // sMisc and the LUT are reused by the next step
+  }
+}
+
 // XOR checksum of decoded outputs (ans/GpuChecksum.cuh:26-93 semantics: XOR of
 // all bytes folded to 8 bits).  grid = (n, Y).
 __global__ void __launch_bounds__(256)
@@ -601,13 +769,14 @@ checksumKernel(DecodeScratch sc) {
 size_t alignUp256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct DecodePlan {
-  size_t members, totals, checksum, archiveChecksum, sizes, total;
+  size_t members, next, totals, checksum, archiveChecksum, sizes, total;
 };
 
 DecodePlan planDecodeScratch(uint32_t n) {
   DecodePlan p{};
   size_t o = 0;
   p.members = o; o = alignUp256(o + sizeof(MemberDesc) * (size_t)n);
+  p.next = o; o = alignUp256(o + 4 * (size_t)n);
   p.totals = o; o = alignUp256(o + 4 * kMaxParts);
   p.checksum = o; o = alignUp256(o + 4 * (size_t)n);
   p.archiveChecksum = o; o = alignUp256(o + 4 * (size_t)n);
@@ -673,25 +842,59 @@ int launchDecode(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t par
   return DGB_OK;
 }
 
-template <int KIND, int PB, int WARPS>
-int launchDecodeV(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t part, uint64_t blockBound,
-                  cudaStream_t stream) {
-  const Options& opt = options();
-  const bool stage = opt.decode_stage != 0, l64 = opt.decode_lut64 != 0;
-  if (stage) {
-    return l64 ? launchDecode<KIND, PB, WARPS, true, true>(sc, m0, m1, part, blockBound, stream)
-               : launchDecode<KIND, PB, WARPS, true, false>(sc, m0, m1, part, blockBound, stream);
-  }
-  return l64 ? launchDecode<KIND, PB, WARPS, false, true>(sc, m0, m1, part, blockBound, stream)
-             : launchDecode<KIND, PB, WARPS, false, false>(sc, m0, m1, part, blockBound, stream);
-}
-
+// One variant is shipped per (kind, probBits): 8 warps per CTA, TMA-staged streams, 4-byte LUT
+// entries.  The alternatives measured in round 1 (4 warps, direct-from-global streams, 8-byte LUT
+// entries) were slower on every workload and are no longer instantiated.
 template <int KIND, int PB>
 int launchDecodeW(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t part, uint64_t blockBound,
                   cudaStream_t stream) {
-  switch (options().decode_warps) {
-    case 8: return launchDecodeV<KIND, PB, 8>(sc, m0, m1, part, blockBound, stream);
-    default: return launchDecodeV<KIND, PB, 4>(sc, m0, m1, part, blockBound, stream);
+  return launchDecode<KIND, PB, 8, true, false>(sc, m0, m1, part, blockBound, stream);
+}
+
+template <int KIND, int PB>
+int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks, uint32_t chunkBlocks,
+                      uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
+                      cudaStream_t stream) {
+  constexpr int WARPS = 8;
+  auto kern = decodeFusedKernel<KIND, PB, WARPS>;
+  // staging slot per warp: worst case for raw bytes; float kinds code exponent-like bytes that
+  // compress well, so a smaller slot (more resident warps) covers them and rare larger blocks
+  // take the direct-from-global path inside the kernel
+  uint32_t slotWords = slotWordsOpt > 0 ? slotWordsOpt : (KIND == kKindBytes ? maxBlockWords(PB) : 1536u);
+  slotWords = std::min(roundUp(slotWords, 8u), maxBlockWords(PB));
+  const size_t smemBytes = (2 * kNumSymbols + 64) * 4 + ((WARPS + 1) & ~1) * 8 +
+                           (size_t)WARPS * kRingSlots * RowWriter<KIND>::kRingSlotBytes +
+                           (size_t)WARPS * (128u + slotWords * 2u);
+  static thread_local int perSm = 0;
+  static thread_local size_t perSmKey = 0;
+  int devOrdinal = 0;
+  DGB_CUDA_TRY(cudaGetDevice(&devOrdinal));
+  const size_t occKey = smemBytes | ((size_t)(devOrdinal + 1) << 40);
+  if (perSm == 0 || perSmKey != occKey) {
+    DGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    int occ = 0;
+    DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smemBytes));
+    perSm = std::max(occ, 1);
+    perSmKey = occKey;
+  }
+  const uint64_t resident = (uint64_t)perSm * smCountD();
+  const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(resident, totalChunks));
+  timerBegin(kSlotDecode, stream);
+  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, n, chunkBlocks, slotWords, outSuccess, outSize, checksum);
+  DGB_CUDA_TRY(cudaGetLastError());
+  timerEnd(kSlotDecode, stream);
+  return DGB_OK;
+}
+
+template <int KIND>
+int decodeFusedKind(const DecodeScratch& sc, int pb, uint32_t n, uint64_t totalChunks, uint32_t chunkBlocks,
+                    uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
+                    cudaStream_t stream) {
+  switch (pb) {
+    case 9: return launchDecodeFused<KIND, 9>(sc, n, totalChunks, chunkBlocks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+    case 10: return launchDecodeFused<KIND, 10>(sc, n, totalChunks, chunkBlocks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+    case 11: return launchDecodeFused<KIND, 11>(sc, n, totalChunks, chunkBlocks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+    default: return DGB_ERR_INVALID_ARG;
   }
 }
 
@@ -723,8 +926,15 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   if (!temp || tempBytes < dp.total) return DGB_ERR_TEMP_TOO_SMALL;
   if (reinterpret_cast<uintptr_t>(temp) & 255u) return DGB_ERR_INVALID_ARG;
 
-  std::vector<MemberDesc> desc(n);
+  const Options opt = options();  // one snapshot per call
+  const bool fused = opt.decode_fused != 0;
+  const uint32_t chunkBlocks = (uint32_t)std::max(1, std::min(opt.decode_chunk_blocks, 4096));
+  static thread_local std::vector<MemberDesc> descStage;  // reused: no allocation on the steady-state path
+  static thread_local std::vector<uint64_t> weightStage;
+  descStage.resize(n);
+  MemberDesc* desc = descStage.data();
   const uint32_t wordBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
+  uint64_t totalChunks = 0;
   for (uint32_t i = 0; i < n; ++i) {
     if (!members[i].in || (members[i].size && !members[i].out)) return DGB_ERR_INVALID_ARG;
     // headers are read as 16 B vectors; the reference imposes the same alignment
@@ -733,57 +943,84 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     desc[i].in = members[i].in;
     desc[i].out = members[i].out;
     desc[i].size = members[i].size;  // capacity
-    desc[i].work0 = 0;
+    // single-launch path: chunk count from the capacity (>= 1: every header is visited once)
+    const uint32_t chunks = std::max(1u, divUp(divUp(members[i].size, kBlockBytes), chunkBlocks));
+    desc[i].work0 = fused ? chunks : 0u;
+    totalChunks += chunks;
   }
   uint8_t* base = static_cast<uint8_t*>(temp);
   DecodeScratch sc;
   sc.members = reinterpret_cast<MemberDesc*>(base + dp.members);
+  sc.next = reinterpret_cast<uint32_t*>(base + dp.next);
   sc.totals = reinterpret_cast<uint32_t*>(base + dp.totals);
   sc.checksum = reinterpret_cast<uint32_t*>(base + dp.checksum);
   sc.archiveChecksum = reinterpret_cast<uint32_t*>(base + dp.archiveChecksum);
   sc.sizes = reinterpret_cast<uint32_t*>(base + dp.sizes);
-  DGB_CUDA_TRY(cudaMemcpyAsync(sc.members, desc.data(), sizeof(MemberDesc) * n,
-                               cudaMemcpyHostToDevice, stream));
+  DGB_CUDA_TRY(cudaMemcpyAsync(sc.members, desc, sizeof(MemberDesc) * n, cudaMemcpyHostToDevice, stream));
   if (checksum) DGB_CUDA_TRY(cudaMemsetAsync(sc.checksum, 0, 4 * (size_t)n, stream));
 
-  // sub-batches on internal streams: the plan kernel (pure latency) of one part hides behind the
-  // decode kernel of another, and the tail of one decode kernel overlaps the next
-  std::vector<uint64_t> weight(n);
-  uint64_t totalBytes = 0;
-  for (uint32_t i = 0; i < n; ++i) { weight[i] = (uint64_t)desc[i].size * wordBytes; totalBytes += weight[i]; }
-  const int parts = autoParts(kind, n, totalBytes, true);
-  uint32_t bounds[kMaxParts + 1];
-  splitParts(weight.data(), n, parts, bounds);
-  StreamPool* pool = nullptr;
-  if (parts > 1) {
-    int prc = streamPool(&pool);
-    if (prc != DGB_OK) return prc;
-    DGB_CUDA_TRY(cudaEventRecord(pool->start, stream));
-  }
-  for (int part = 0; part < parts; ++part) {
-    const uint32_t m0 = bounds[part], m1 = bounds[part + 1];
-    if (m1 == m0) continue;
-    cudaStream_t ps = stream;
-    if (parts > 1) {
-      ps = pool->s[part];
-      DGB_CUDA_TRY(cudaStreamWaitEvent(ps, pool->start, 0));
-    }
-    uint64_t partBound = 0;
-    for (uint32_t i = m0; i < m1; ++i) partBound += divUp(desc[i].size, kBlockBytes);
+  if (fused) {
+    DGB_CUDA_TRY(cudaMemsetAsync(sc.next, 0, 4 * (size_t)n, stream));
+    const uint32_t slotOpt = opt.decode_slot_words > 0 ? (uint32_t)opt.decode_slot_words : 0u;
     int rc;
     switch (kind) {
-      case kKindBytes: rc = decodeKind<kKindBytes>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
-      case kKindF16: rc = decodeKind<kKindF16>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
-      case kKindBF16: rc = decodeKind<kKindBF16>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
-      case kKindF32: rc = decodeKind<kKindF32>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+      case kKindBytes: rc = decodeFusedKind<kKindBytes>(sc, pb, n, totalChunks, chunkBlocks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
+      case kKindF16: rc = decodeFusedKind<kKindF16>(sc, pb, n, totalChunks, chunkBlocks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
+      case kKindBF16: rc = decodeFusedKind<kKindBF16>(sc, pb, n, totalChunks, chunkBlocks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
+      case kKindF32: rc = decodeFusedKind<kKindF32>(sc, pb, n, totalChunks, chunkBlocks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
       default: return DGB_ERR_INVALID_ARG;
     }
     if (rc != DGB_OK) return rc;
+  } else {
+    // two-kernel path: sub-batches on internal streams: the plan kernel (pure latency) of one part
+    // hides behind the decode kernel of another, and the tail of one decode kernel overlaps the next
+    weightStage.resize(n);
+    uint64_t totalBytes = 0;
+    for (uint32_t i = 0; i < n; ++i) { weightStage[i] = (uint64_t)desc[i].size * wordBytes; totalBytes += weightStage[i]; }
+    const int parts = autoParts(kind, n, totalBytes, true);
+    uint32_t bounds[kMaxParts + 1];
+    splitParts(weightStage.data(), n, parts, bounds);
+    // joins the helper streams on every exit path (the caller reuses its scratch on return)
+    struct Join {
+      StreamPool* pool = nullptr;
+      cudaStream_t stream = nullptr;
+      bool forked[kMaxParts] = {};
+      ~Join() {
+        if (!pool) return;
+        for (int k = 0; k < kMaxParts; ++k)
+          if (forked[k] && cudaEventRecord(pool->done[k], pool->s[k]) == cudaSuccess) cudaStreamWaitEvent(stream, pool->done[k], 0);
+      }
+    } join;
+    StreamPool* pool = nullptr;
     if (parts > 1) {
-      DGB_CUDA_TRY(cudaEventRecord(pool->done[part], ps));
-      DGB_CUDA_TRY(cudaStreamWaitEvent(stream, pool->done[part], 0));
+      int prc = streamPool(&pool);
+      if (prc != DGB_OK) return prc;
+      DGB_CUDA_TRY(cudaEventRecord(pool->start, stream));
+      join.pool = pool;
+      join.stream = stream;
     }
-  }
+    for (int part = 0; part < parts; ++part) {
+      const uint32_t m0 = bounds[part], m1 = bounds[part + 1];
+      if (m1 == m0) continue;
+      cudaStream_t ps = stream;
+      if (parts > 1) {
+        ps = pool->s[part];
+        DGB_CUDA_TRY(cudaStreamWaitEvent(ps, pool->start, 0));
+        join.forked[part] = true;
+      }
+      uint64_t partBound = 0;
+      for (uint32_t i = m0; i < m1; ++i) partBound += divUp(desc[i].size, kBlockBytes);
+      int rc;
+      switch (kind) {
+        case kKindBytes: rc = decodeKind<kKindBytes>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+        case kKindF16: rc = decodeKind<kKindF16>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+        case kKindBF16: rc = decodeKind<kKindBF16>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+        case kKindF32: rc = decodeKind<kKindF32>(sc, pb, checksum, m0, m1, part, partBound, outSuccess_dev, outSize_dev, ps); break;
+        default: return DGB_ERR_INVALID_ARG;
+      }
+      if (rc != DGB_OK) return rc;
+    }
+  }  // ~Join orders the helper streams before the caller's stream
 
   if (checksum) {
     // ans/GpuANSDecode.cuh:555-591 / float/GpuFloatDecompress.cuh:698-733: checksum the

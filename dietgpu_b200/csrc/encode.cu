@@ -60,6 +60,9 @@ struct EncodeScratch {
   bool wideTable;                 // entry format: EncEntryWide (16 B) or EncEntry (8 B)
   uint8_t* compRows;              // float kinds: [n] rows of compStride bytes
   uint32_t compStride;
+  // fused single-launch encoder only
+  const uint2* workIdx;           // [n + 1] {first stats item, first encode chunk} of member i
+  uint32_t* ready;                // [n]  (zeroed) 1 once the member's table is published
 };
 
 // ---------------------------------------------------------------------------
@@ -216,11 +219,26 @@ __device__ bool flushAndTicket(uint32_t (*sHist)[kNumSymbols], uint32_t* histGlo
 // K1 (bytes): histogram + checksum + normalisation epilogue.
 // grid = (n, Y): CTA (m, y) walks slabs y, y+Y, ... of member m.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStatsThreads)
-statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, int pb,
-                 bool useChecksum, uint32_t slabVecs, uint32_t memberBase, uint32_t* __restrict__ outSize) {
-  __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
-  const uint32_t m = blockIdx.x + memberBase, t = threadIdx.x, warp = t >> 5;
+// Slab accounting shared by host (work-item counts of the fused launch) and device.
+__host__ __device__ inline uint32_t bytesHeadLen(const void* in, uint32_t size) {
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15u);
+  const uint32_t head = (16u - mis) & 15u;
+  return size < head ? size : head;
+}
+__host__ __device__ inline uint32_t bytesSlabs(const void* in, uint32_t size, uint32_t slabVecs, bool doPass) {
+  if (!doPass) return 0u;
+  const uint32_t nVec = (size - bytesHeadLen(in, size)) / 16u;
+  const uint32_t s = divUp(nVec, slabVecs);
+  return s > 0u ? s : (size > 0u ? 1u : 0u);
+}
+
+// Work of CTA y of Y on member m (Y = gridDim.y of the two-kernel path, the member's item count in
+// the fused kernel).  Returns true in the CTA that finished the member (its table is published).
+__device__ __forceinline__ bool statsBytesItem(const EncodeScratch& sc, uint32_t (*sHist)[kNumSymbols],
+                                               const uint32_t* __restrict__ histogramGiven, int pb,
+                                               bool useChecksum, uint32_t slabVecs, uint32_t m, uint32_t y,
+                                               uint32_t Y, uint32_t* __restrict__ outSize) {
+  const uint32_t t = threadIdx.x, warp = t >> 5;
   const MemberDesc md = sc.members[m];
   const uint8_t* in = static_cast<const uint8_t*>(md.in);
   const uint32_t size = md.size;
@@ -229,28 +247,27 @@ statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, 
   const bool doPass = doHist || useChecksum;
 
   // member = [head bytes | 16 B vectors | tail bytes]
-  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15u);
-  const uint32_t head = min(size, (16u - mis) & 15u);
+  const uint32_t head = bytesHeadLen(in, size);
   const uint32_t nVec = (size - head) / 16u;
   const uint32_t tail = size - head - nVec * 16u;
-  const uint32_t nSlabs = doPass ? max(divUp(nVec, slabVecs), size > 0 ? 1u : 0u) : 0u;
-  const uint32_t participants = min(nSlabs, gridDim.y);
+  const uint32_t nSlabs = bytesSlabs(in, size, slabVecs, doPass);
+  const uint32_t participants = min(nSlabs, Y);
 
   if (participants == 0) {
-    if (blockIdx.y != 0) return;
+    if (y != 0) return false;
   } else {
-    if (blockIdx.y >= participants) return;
+    if (y >= participants) return false;
 #pragma unroll
     for (int w = 0; w < kStatsWarps; ++w) sHist[w][t] = 0;
     __syncthreads();
     uint32_t* wh = sHist[warp];
     uint32_t xorAcc = 0;
-    if (blockIdx.y == 0) {
+    if (y == 0) {
       if (t < head) { uint32_t b = in[t]; atomicAdd(&wh[b], 1u); xorAcc ^= b; }
       if (t < tail) { uint32_t b = in[head + nVec * 16u + t]; atomicAdd(&wh[b], 1u); xorAcc ^= b; }
     }
     const uint4* vec = reinterpret_cast<const uint4*>(in + head);
-    for (uint32_t slab = blockIdx.y; slab < nSlabs; slab += gridDim.y) {
+    for (uint32_t slab = y; slab < nSlabs; slab += Y) {
       const uint32_t v0 = slab * slabVecs, v1 = min(nVec, v0 + slabVecs);
       for (uint32_t i0 = v0 + t; i0 < v1; i0 += kStatsUnroll * kStatsThreads) {
         uint4 vv[kStatsUnroll];
@@ -279,16 +296,25 @@ statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, 
     }
     if (!flushAndTicket(sHist, sc.hist + m * kNumSymbols, sc.histDone + m, participants, doHist,
                         xorAcc, sc.checksum + m, useChecksum))
-      return;
+      return false;
   }
 
   // ---- last CTA of the member ----
   if (size == 0) {
     publishEmptyMember(archive, pb, useChecksum, outSize, m, 0);
-    return;
+    return true;
   }
   const uint32_t* h = doHist ? sc.hist + m * kNumSymbols : histogramGiven + m * kNumSymbols;
   normalizeAndPublish(h, size, pb, sc.wideTable, sc.table + m * kNumSymbols, archive);
+  return true;
+}
+
+__global__ void __launch_bounds__(kStatsThreads)
+statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, int pb,
+                 bool useChecksum, uint32_t slabVecs, uint32_t memberBase, uint32_t* __restrict__ outSize) {
+  __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
+  statsBytesItem(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y,
+                 gridDim.y, outSize);
 }
 
 // ---------------------------------------------------------------------------
@@ -309,14 +335,78 @@ __device__ __forceinline__ uint32_t rot16x2(uint32_t w) {
   return w;
 }
 
+// Stores of 8 / 4 consecutive bytes at an address that is only guaranteed the alignment of the
+// member's first vector (members whose input is not 16 B aligned shift every plane by `head`
+// elements).  The alignment is the same for every vector of a member, so the branch is uniform.
+__device__ __forceinline__ void storeBytes8(uint8_t* dst, uint2 v) {
+  const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 7u);
+  if (a == 0) {
+    *reinterpret_cast<uint2*>(dst) = v;
+  } else if ((a & 3u) == 0) {
+    reinterpret_cast<uint32_t*>(dst)[0] = v.x;
+    reinterpret_cast<uint32_t*>(dst)[1] = v.y;
+  } else if ((a & 1u) == 0) {
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+    d[0] = (uint16_t)v.x; d[1] = (uint16_t)(v.x >> 16); d[2] = (uint16_t)v.y; d[3] = (uint16_t)(v.y >> 16);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { dst[k] = (uint8_t)(v.x >> (8 * k)); dst[4 + k] = (uint8_t)(v.y >> (8 * k)); }
+  }
+}
+__device__ __forceinline__ void storeBytes4(uint8_t* dst, uint32_t v) {
+  const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
+  if (a == 0) {
+    *reinterpret_cast<uint32_t*>(dst) = v;
+  } else if ((a & 1u) == 0) {
+    reinterpret_cast<uint16_t*>(dst)[0] = (uint16_t)v;
+    reinterpret_cast<uint16_t*>(dst)[1] = (uint16_t)(v >> 16);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = (uint8_t)(v >> (8 * k));
+  }
+}
+
+// member = [head elements up to the first 16 B boundary | 16 B vectors | tail elements]
+__host__ __device__ inline uint32_t floatHeadLen(const void* in, uint32_t size, uint32_t wordBytes) {
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15u);
+  const uint32_t head = ((16u - mis) & 15u) / wordBytes;
+  return size < head ? size : head;
+}
+__host__ __device__ inline uint32_t floatSlabs(const void* in, uint32_t size, uint32_t wordBytes, uint32_t slabVecs) {
+  if (size == 0) return 0u;
+  const uint32_t nVec = (size - floatHeadLen(in, size, wordBytes)) / (16u / wordBytes);
+  const uint32_t s = divUp(nVec, slabVecs);
+  return s > 0u ? s : 1u;
+}
+
 template <int FT>
-__global__ void __launch_bounds__(kStatsThreads)
-statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, uint32_t memberBase,
-                 uint32_t* __restrict__ outSize) {
-  __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
+__device__ __forceinline__ uint32_t splitScalar(const uint8_t* in, uint32_t e, uint8_t* comp, uint8_t* non,
+                                                uint32_t size) {
+  uint32_t c;
+  if (FT == DGB_FLOAT32) {
+    uint32_t w = reinterpret_cast<const uint32_t*>(in)[e];
+    w = __funnelshift_l(w, w, 1);
+    c = w >> 24;
+    reinterpret_cast<uint16_t*>(non)[e] = (uint16_t)(w & 0xffffu);
+    (non + 2u * roundUp(size, 8u))[e] = (uint8_t)((w >> 16) & 0xffu);
+  } else {
+    uint32_t w = reinterpret_cast<const uint16_t*>(in)[e];
+    if (FT == DGB_BFLOAT16) w = ((w << 1) | (w >> 15)) & 0xffffu;
+    c = w >> 8;
+    non[e] = (uint8_t)(w & 0xffu);
+  }
+  comp[e] = (uint8_t)c;
+  return c;
+}
+
+// Work of CTA y of Y on member m; returns true in the CTA that finished the member.
+template <int FT>
+__device__ __forceinline__ bool statsFloatItem(const EncodeScratch& sc, uint32_t (*sHist)[kNumSymbols], int pb,
+                                               bool useChecksum, uint32_t slabVecs, uint32_t m, uint32_t y,
+                                               uint32_t Y, uint32_t* __restrict__ outSize) {
   constexpr uint32_t EPV = (FT == DGB_FLOAT32) ? 4u : 8u;  // elements per 16 B vector
   constexpr uint32_t WB = (FT == DGB_FLOAT32) ? 4u : 2u;   // word bytes
-  const uint32_t m = blockIdx.x + memberBase, t = threadIdx.x, warp = t >> 5;
+  const uint32_t t = threadIdx.x, warp = t >> 5;
   const MemberDesc md = sc.members[m];
   const uint8_t* in = static_cast<const uint8_t*>(md.in);
   const uint32_t size = md.size;  // float words
@@ -326,15 +416,15 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
   uint8_t* ansArchive = non + nonBytes;
   uint8_t* comp = sc.compRows + (size_t)m * sc.compStride;
 
-  const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
-  const uint32_t nVec = aligned ? size / EPV : 0u;
-  const uint32_t nSlabs = size > 0 ? max(divUp(nVec, slabVecs), 1u) : 0u;
-  const uint32_t participants = min(nSlabs, gridDim.y);
+  const uint32_t head = floatHeadLen(in, size, WB);
+  const uint32_t nVec = (size - head) / EPV;
+  const uint32_t nSlabs = floatSlabs(in, size, WB, slabVecs);
+  const uint32_t participants = min(nSlabs, Y);
 
   if (participants == 0) {
-    if (blockIdx.y != 0) return;
+    if (y != 0) return false;
   } else {
-    if (blockIdx.y >= participants) return;
+    if (y >= participants) return false;
 #pragma unroll
     for (int w = 0; w < kStatsWarps; ++w) sHist[w][t] = 0;
     __syncthreads();
@@ -342,8 +432,11 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
     uint32_t xorAcc = 0;
 
     // ---- vector body ----
-    const uint4* vec = reinterpret_cast<const uint4*>(in);
-    for (uint32_t slab = blockIdx.y; slab < nSlabs; slab += gridDim.y) {
+    const uint4* vec = reinterpret_cast<const uint4*>(in + (size_t)head * WB);
+    uint8_t* compV = comp + head;                 // plane positions of the first vector
+    uint8_t* nonV = non + (size_t)head * (FT == DGB_FLOAT32 ? 2u : 1u);
+    uint8_t* non1V = non + 2u * roundUp(size, 8u) + head;  // fp32: the u8 plane
+    for (uint32_t slab = y; slab < nSlabs; slab += Y) {
       const uint32_t v0 = slab * slabVecs, v1 = min(nVec, v0 + slabVecs);
       // four independent 16 B loads per thread are issued before any of them is consumed: the
       // kernel is a pure stream and was latency-bound with one load in flight (ncu: 75 % of stall
@@ -365,15 +458,15 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
             const uint32_t r2 = __funnelshift_l(v.z, v.z, 1), r3 = __funnelshift_l(v.w, v.w, 1);
             // comp = top byte of each rotated word
             const uint32_t c = __byte_perm(__byte_perm(r0, r1, 0x0073), __byte_perm(r2, r3, 0x0073), 0x5410);
-            reinterpret_cast<uint32_t*>(comp)[i] = c;
+            storeBytes4(compV + 4u * (size_t)i, c);
             // u16 plane: low halves
             uint2 lo;
             lo.x = __byte_perm(r0, r1, 0x5410);
             lo.y = __byte_perm(r2, r3, 0x5410);
-            reinterpret_cast<uint2*>(non)[i] = lo;
+            storeBytes8(nonV + 8u * (size_t)i, lo);
             // u8 plane: byte 2 of each
             const uint32_t hi = __byte_perm(__byte_perm(r0, r1, 0x0062), __byte_perm(r2, r3, 0x0062), 0x5410);
-            reinterpret_cast<uint32_t*>(non + 2u * roundUp(size, 8u))[i] = hi;
+            storeBytes4(non1V + 4u * (size_t)i, hi);
             atomicAdd(&wh[c & 0xffu], 1u);
             atomicAdd(&wh[(c >> 8) & 0xffu], 1u);
             atomicAdd(&wh[(c >> 16) & 0xffu], 1u);
@@ -386,8 +479,8 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
             c.y = __byte_perm(r2, r3, 0x7531);
             nn.x = __byte_perm(r0, r1, 0x6420);
             nn.y = __byte_perm(r2, r3, 0x6420);
-            reinterpret_cast<uint2*>(comp)[i] = c;
-            reinterpret_cast<uint2*>(non)[i] = nn;
+            storeBytes8(compV + 8u * (size_t)i, c);
+            storeBytes8(nonV + 8u * (size_t)i, nn);
             atomicAdd(&wh[c.x & 0xffu], 1u);
             atomicAdd(&wh[(c.x >> 8) & 0xffu], 1u);
             atomicAdd(&wh[(c.x >> 16) & 0xffu], 1u);
@@ -400,32 +493,11 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
         }
       }
     }
-    // ---- scalar remainder (and the whole member when not 16 B aligned) ----
-    const uint32_t scalarStart = nVec * EPV;
-    const uint32_t scalarCount = size - scalarStart;
-    if (scalarCount) {
-      // spread the scalar work over the participating CTAs
-      for (uint32_t i = blockIdx.y * kStatsThreads + t; i < scalarCount;
-           i += participants * kStatsThreads) {
-        const uint32_t e = scalarStart + i;
-        uint32_t c;
-        if (FT == DGB_FLOAT32) {
-          uint32_t w = reinterpret_cast<const uint32_t*>(in)[e];
-          w = __funnelshift_l(w, w, 1);
-          c = w >> 24;
-          reinterpret_cast<uint16_t*>(non)[e] = (uint16_t)(w & 0xffffu);
-          (non + 2u * roundUp(size, 8u))[e] = (uint8_t)((w >> 16) & 0xffu);
-        } else {
-          uint32_t w = reinterpret_cast<const uint16_t*>(in)[e];
-          if (FT == DGB_BFLOAT16) w = ((w << 1) | (w >> 15)) & 0xffffu;
-          c = w >> 8;
-          non[e] = (uint8_t)(w & 0xffu);
-        }
-        comp[e] = (uint8_t)c;
-        atomicAdd(&wh[c], 1u);
-      }
-    }
-    if (blockIdx.y == 0) {
+    if (y == 0) {
+      // ---- scalar head and tail (fewer than one vector each) ----
+      const uint32_t tailStart = head + nVec * EPV;
+      if (t < head) atomicAdd(&wh[splitScalar<FT>(in, t, comp, non, size)], 1u);
+      if (t < size - tailStart) atomicAdd(&wh[splitScalar<FT>(in, tailStart + t, comp, non, size)], 1u);
       // float header (float/GpuFloatCompress.cuh:324-337) and zero padding of the planes
       if (t == 0) {
         // float-level checksum is patched in by the epilogue CTA
@@ -443,13 +515,12 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
     if (useChecksum) {
       // the float checksum covers the first `size` BYTES only
       const uint32_t cbytes = size;  // bytes, not words
-      for (uint32_t i = blockIdx.y * kStatsThreads + t; i < cbytes; i += participants * kStatsThreads)
+      for (uint32_t i = y * kStatsThreads + t; i < cbytes; i += participants * kStatsThreads)
         xorAcc ^= in[i];
     }
-    (void)WB;
     if (!flushAndTicket(sHist, sc.hist + m * kNumSymbols, sc.histDone + m, participants, true,
                         xorAcc, sc.checksum + m, useChecksum))
-      return;
+      return false;
   }
 
   // ---- last CTA of the member ----
@@ -459,12 +530,21 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
           make_uint4(kFloatMagicVersion, 0u, (uint32_t)FT | ((useChecksum ? 1u : 0u) << 4), 0u);
     }
     publishEmptyMember(ansArchive, pb, false, outSize, m, kFloatHeaderBytes + nonBytes);
-    return;
+    return true;
   }
   if (useChecksum && t == 0) {
     reinterpret_cast<uint32_t*>(archive)[3] = __ldcg(sc.checksum + m);
   }
   normalizeAndPublish(sc.hist + m * kNumSymbols, size, pb, sc.wideTable, sc.table + m * kNumSymbols, ansArchive);
+  return true;
+}
+
+template <int FT>
+__global__ void __launch_bounds__(kStatsThreads)
+statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, uint32_t memberBase,
+                 uint32_t* __restrict__ outSize) {
+  __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
+  statsFloatItem<FT>(sc, sHist, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y, gridDim.y, outSize);
 }
 
 // ---------------------------------------------------------------------------
@@ -919,6 +999,94 @@ __host__ __device__ constexpr uint32_t encFastWarpSmem(uint32_t slotWords) {
   return kEncRingSlots * kEncGroupRows * 32u + slotWords * 2u;  // ring + staging
 }
 
+// Per-warp view of the CTA's dynamic shared memory: [input ring | staging slot] per warp.
+struct WarpSmem {
+  uint32_t ringAddr, stageAddr;
+  uint16_t* stage;
+  Spill sp;
+};
+__device__ __forceinline__ WarpSmem warpSmem(const EncodeScratch& sc, uint8_t* smem, uint32_t warp, uint32_t W,
+                                             uint32_t slotWords, int pb, uint32_t spillWarpBase) {
+  WarpSmem ws;
+  uint8_t* mine = smem + (size_t)warp * encFastWarpSmem(slotWords);
+  ws.ringAddr = smemAddr(mine);
+  ws.sp.area = slotWords < maxBlockWords(pb)
+                   ? reinterpret_cast<uint16_t*>(sc.spill) + (size_t)(spillWarpBase + blockIdx.x * W + warp) * maxBlockWords(pb)
+                   : nullptr;
+  ws.sp.limitBytes = (slotWords - kEncGroupRows * 32u - 8u) * 2u;  // a group emits at most 16*32 words
+  ws.sp.spilled = 0;
+  ws.stage = reinterpret_cast<uint16_t*>(mine + kEncRingSlots * kEncGroupRows * 32u);
+  ws.stageAddr = smemAddr(ws.stage);
+  return ws;
+}
+
+// Loads member m's encoder table (written by the statistics epilogue) into the CTA's table slot.
+template <bool WIDE>
+__device__ __forceinline__ void loadTable(const EncodeScratch& sc, uint4* sTab, uint32_t m) {
+  const uint4* src = sc.table + (size_t)m * kNumSymbols;
+  for (uint32_t i = threadIdx.x; i < (WIDE ? kNumSymbols : kNumSymbols / 2); i += blockDim.x) sTab[i] = __ldcg(src + i);
+}
+
+// Warps of the CTA encode blocks [first, last) of member m (block k by warp (k - first) % W): the
+// 32-lane rANS state machine per block, then the block takes its place in the archive's data
+// section with one 64-bit atomic.
+template <bool WIDE>
+__device__ __forceinline__ void encodeMemberBlocks(const EncodeScratch& sc, const MemberDesc& md, uint32_t m,
+                                                   uint32_t first, uint32_t last, int kind, int pb,
+                                                   bool useChecksum, uint32_t tabAddr, WarpSmem& ws,
+                                                   uint32_t warp, uint32_t W, uint32_t lane,
+                                                   uint32_t* __restrict__ outSize) {
+  const uint32_t size = md.size;
+  const uint32_t nb = divUp(size, kBlockBytes);
+  const uint8_t* ansIn;
+  uint8_t* ansOut;
+  uint32_t extraBytes = 0;
+  if (kind == kKindBytes) {
+    ansIn = static_cast<const uint8_t*>(md.in);
+    ansOut = static_cast<uint8_t*>(md.out);
+  } else {
+    ansIn = sc.compRows + (size_t)m * sc.compStride;
+    extraBytes = kFloatHeaderBytes + floatNonCompBytes(kind, size);
+    ansOut = static_cast<uint8_t*>(md.out) + extraBytes;
+  }
+  __builtin_assume(__isGlobal(ansIn));
+  __builtin_assume(__isGlobal(ansOut));
+  uint8_t* pStates = ansOut + kAnsHeaderBytes + kAnsPdfBytes;
+  uint8_t* pBlockWords = pStates + 128u * nb;
+  uint8_t* pData = pBlockWords + 8u * roundUp(nb, 2u);
+
+  for (uint32_t block = first + warp; block < last; block += W) {
+    const uint32_t start = block * kBlockBytes;
+    const uint32_t blockLen = min(kBlockBytes, size - start);
+    uint32_t state;
+    const uint32_t words = encodeBlockWarp<WIDE>(ansIn + start, blockLen, tabAddr, pb, ws.stageAddr, ws.stage, ws.sp,
+                                                 ws.ringAddr, lane, state);
+    const uint32_t padded = roundUp(words, 8u);
+    // take a place in the data section: one 64-bit atomic hands out the word offset (low half)
+    // and counts finished blocks (high half), so no fence is needed to order the two
+    unsigned long long old = 0;
+    if (lane == 0) old = atomicAdd(sc.allocDone + m, (1ull << 32) | (unsigned long long)padded);
+    reinterpret_cast<uint32_t*>(pStates)[block * 32u + lane] = state;
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const uint32_t base = (uint32_t)old;
+    if (lane == 0)
+      reinterpret_cast<uint2*>(pBlockWords)[block] = make_uint2((blockLen << 16) | words, base);
+    placeStream(ws.stage, ws.sp, words, padded, pData + 2u * (size_t)base, lane);
+    // the block that takes the last place knows the member's total and writes the header
+    if (lane == 0 && (uint32_t)(old >> 32) == nb - 1u) {
+      const uint32_t totalWords = base + padded;
+      uint4* h = reinterpret_cast<uint4*>(ansOut);
+      h[0] = make_uint4(kAnsMagicVersion, nb, size, totalWords);
+      const bool ansChecksum = useChecksum && kind == kKindBytes;
+      h[1] = make_uint4((uint32_t)pb | ((ansChecksum ? 1u : 0u) << 4),
+                        ansChecksum ? __ldcg(sc.checksum + m) : 0u, 0u, 0u);
+      if (nb & 1u) reinterpret_cast<uint2*>(pBlockWords)[nb] = make_uint2(0u, 0u);
+      if (outSize) outSize[m] = ansOverhead(nb) + 2u * totalWords + extraBytes;
+    }
+    __syncwarp();  // staging and ring are reused by the next block
+  }
+}
+
 template <bool WIDE>
 __global__ void
 encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
@@ -931,16 +1099,7 @@ encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
   const uint32_t t = threadIdx.x, lane = t & 31u;
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
   const uint32_t W = blockDim.x >> 5;
-  uint8_t* mine = smem + (size_t)warp * encFastWarpSmem(slotWords);
-  const uint32_t ringAddr = smemAddr(mine);
-  Spill sp;
-  sp.area = slotWords < maxBlockWords(pb)
-                ? reinterpret_cast<uint16_t*>(sc.spill) + (size_t)(spillWarpBase + blockIdx.x * W + warp) * maxBlockWords(pb)
-                : nullptr;
-  sp.limitBytes = (slotWords - kEncGroupRows * 32u - 8u) * 2u;  // a group emits at most 16*32 words
-  sp.spilled = 0;
-  uint16_t* myStage = reinterpret_cast<uint16_t*>(mine + kEncRingSlots * kEncGroupRows * 32u);
-  const uint32_t stageAddr = smemAddr(myStage);
+  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, spillWarpBase);
   const uint32_t tabAddr = smemAddr(sTab);
 
   const uint64_t g = gridDim.x, span = blockEnd - blockBegin;
@@ -959,96 +1118,137 @@ encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
     __syncthreads();
     const uint32_t m = sMember;
     const MemberDesc md = sc.members[m];
-    const uint32_t size = md.size;
-    const uint32_t nb = divUp(size, kBlockBytes);
+    const uint32_t nb = divUp(md.size, kBlockBytes);
     const uint32_t memberEnd = min(end, md.work0 + nb);
-    {
-      const uint4* src = sc.table + (size_t)m * kNumSymbols;
-      for (uint32_t i = t; i < (WIDE ? kNumSymbols : kNumSymbols / 2); i += blockDim.x) sTab[i] = __ldcg(src + i);
-    }
+    loadTable<WIDE>(sc, sTab, m);
     __syncthreads();
-
-    const uint8_t* ansIn;
-    uint8_t* ansOut;
-    uint32_t extraBytes = 0;
-    if (kind == kKindBytes) {
-      ansIn = static_cast<const uint8_t*>(md.in);
-      ansOut = static_cast<uint8_t*>(md.out);
-    } else {
-      ansIn = sc.compRows + (size_t)m * sc.compStride;
-      extraBytes = kFloatHeaderBytes + floatNonCompBytes(kind, size);
-      ansOut = static_cast<uint8_t*>(md.out) + extraBytes;
-    }
-    __builtin_assume(__isGlobal(ansIn));
-    __builtin_assume(__isGlobal(ansOut));
-    uint8_t* pStates = ansOut + kAnsHeaderBytes + kAnsPdfBytes;
-    uint8_t* pBlockWords = pStates + 128u * nb;
-    uint8_t* pData = pBlockWords + 8u * roundUp(nb, 2u);
-
-    for (uint32_t fb = cur + warp; fb < memberEnd; fb += W) {
-      const uint32_t block = fb - md.work0;
-      const uint32_t start = block * kBlockBytes;
-      const uint32_t blockLen = min(kBlockBytes, size - start);
-      uint32_t state;
-      const uint32_t words = encodeBlockWarp<WIDE>(ansIn + start, blockLen, tabAddr, pb, stageAddr, myStage, sp, ringAddr, lane, state);
-      const uint32_t padded = roundUp(words, 8u);
-      // take a place in the data section: one 64-bit atomic hands out the word offset (low half)
-      // and counts finished blocks (high half), so no fence is needed to order the two
-      unsigned long long old = 0;
-      if (lane == 0) old = atomicAdd(sc.allocDone + m, (1ull << 32) | (unsigned long long)padded);
-      reinterpret_cast<uint32_t*>(pStates)[block * 32u + lane] = state;
-      old = __shfl_sync(0xffffffffu, old, 0);
-      const uint32_t base = (uint32_t)old;
-      if (lane == 0)
-        reinterpret_cast<uint2*>(pBlockWords)[block] = make_uint2((blockLen << 16) | words, base);
-      placeStream(myStage, sp, words, padded, pData + 2u * (size_t)base, lane);
-      // the block that takes the last place knows the member's total and writes the header
-      if (lane == 0 && (uint32_t)(old >> 32) == nb - 1u) {
-        const uint32_t totalWords = base + padded;
-        uint4* h = reinterpret_cast<uint4*>(ansOut);
-        h[0] = make_uint4(kAnsMagicVersion, nb, size, totalWords);
-        const bool ansChecksum = useChecksum && kind == kKindBytes;
-        h[1] = make_uint4((uint32_t)pb | ((ansChecksum ? 1u : 0u) << 4),
-                          ansChecksum ? __ldcg(sc.checksum + m) : 0u, 0u, 0u);
-        if (nb & 1u) reinterpret_cast<uint2*>(pBlockWords)[nb] = make_uint2(0u, 0u);
-        if (outSize) outSize[m] = ansOverhead(nb) + 2u * totalWords + extraBytes;
-      }
-      __syncwarp();  // staging and ring are reused by the next block
-    }
+    encodeMemberBlocks<WIDE>(sc, md, m, cur - md.work0, memberEnd - md.work0, kind, pb, useChecksum, tabAddr, ws,
+                             warp, W, lane, outSize);
     cur = memberEnd;
     __syncthreads();  // table is replaced for the next member
   }
 }
 
-size_t alignUp256(size_t v) { return (v + 255) & ~size_t(255); }
-
-// upper bound on resident encoder warps (64 per SM on up to 160 SMs): sizes the spill area
-constexpr uint32_t kMaxSpillWarps = 64u * 160u;
-
-struct ScratchPlan {
-  size_t members, zeroBegin, hist, histDone, checksum, ticket, allocDone, lookback, zeroEnd, table, spill, compRows, total;
-  uint32_t compStride;
-};
-
-ScratchPlan planScratch(int kind, uint32_t n, uint32_t maxSize, uint32_t totalTickets) {
-  ScratchPlan p{};
-  size_t o = 0;
-  p.members = o; o = alignUp256(o + sizeof(MemberDesc) * (size_t)n);
-  p.zeroBegin = o;
-  p.hist = o; o = alignUp256(o + sizeof(uint32_t) * kNumSymbols * (size_t)n);
-  p.histDone = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
-  p.checksum = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
-  p.ticket = o; o = alignUp256(o + 16);
-  p.allocDone = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)n);
-  p.lookback = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)totalTickets);
-  p.zeroEnd = o;
-  p.table = o; o = alignUp256(o + sizeof(uint4) * kNumSymbols * (size_t)n);
-  p.spill = o; o = alignUp256(o + (size_t)kMaxSpillWarps * maxBlockWords(11) * 2u);
-  p.compStride = kind == kKindBytes ? 0u : roundUp(maxSize, 16u);
-  p.compRows = o; o = alignUp256(o + (size_t)p.compStride * n);
-  p.total = o;
-  return p;
+// ---------------------------------------------------------------------------
+// Fused single-launch encoder (default).  One persistent grid; every CTA picks, at each step, one
+// of two kinds of work from two global counters:
+//   * a STATISTICS item  = one slab of one member (the body of K1 above: histogram (+ split, +
+//     checksum); the CTA that finishes a member normalises, publishes pdf + table and sets the
+//     member's `ready` flag), or
+//   * an ENCODE chunk    = a run of 4 KiB blocks of one member (the body of K2), which needs the
+//     member's flag.
+// Chunks are claimed in member order, and a CTA whose chunk is not ready yet works on statistics
+// items (which have no dependencies) instead of waiting, so the HBM-latency-bound statistics pass
+// and the issue-bound coder share every SM and balance themselves; one CTA in `statsEvery` prefers
+// statistics so that the tables stay ahead of the coders.  Progress never depends on co-residency:
+// a claimed item is always held by a running CTA, and the only wait (chunk claimed, member not
+// ready, no statistics left to claim) is for items other running CTAs hold.
+// The reference runs 7-10 kernels for this; its README lists a single cooperative
+// kernel as a next step (README.md:103).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ldAcquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
+__device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+enum FusedAct : uint32_t { kActExit = 0, kActWait = 1, kActStats = 2, kActEncode = 3 };
+constexpr uint32_t kNoChunk = 0xffffffffu;
+
+template <int KIND, bool WIDE>
+__global__ void __launch_bounds__(kStatsThreads, 4)
+encodeFusedKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, int pb, bool useChecksum,
+                  uint32_t numMembers, uint32_t totalItems, uint32_t totalChunks, uint32_t slabVecs,
+                  uint32_t chunkBlocks, uint32_t slotWords, uint32_t statsEvery,
+                  uint32_t* __restrict__ outSize) {
+  // dynamic shared memory: per-warp [ring | staging slot] while encoding, the per-warp histograms
+  // while a statistics item runs (never both: the roles alternate between CTA-wide barriers)
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(16) uint4 sTab[WIDE ? kNumSymbols : kNumSymbols / 2];
+  __shared__ uint32_t sCtl[8];
+  uint32_t (*sHist)[kNumSymbols] = reinterpret_cast<uint32_t (*)[kNumSymbols]>(smem);
+  const uint32_t t = threadIdx.x, lane = t & 31u;
+  const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  constexpr uint32_t W = kStatsThreads / 32;
+  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, 0u);
+  const uint32_t tabAddr = smemAddr(sTab);
+  const bool preferStats = statsEvery != 0u && (blockIdx.x % statsEvery) == 0u;
+
+  // claim state (meaningful in thread 0; the decision is broadcast through sCtl)
+  uint32_t chunk = kNoChunk, chunkMember = 0, itemMember = 0;
+  bool chunksLeft = totalChunks != 0u, statsLeft = totalItems != 0u;
+  uint32_t tabMember = 0xffffffffu;
+
+  for (;;) {
+    if (t == 0) {
+      uint32_t act = kActWait, arg = 0, m = 0;
+      uint32_t item = 0xffffffffu;
+      if (preferStats && statsLeft) {
+        item = atomicAdd(sc.ticket + 0, 1u);
+        if (item >= totalItems) { statsLeft = false; item = 0xffffffffu; }
+      }
+      if (item == 0xffffffffu) {
+        if (chunk == kNoChunk && chunksLeft) {
+          chunk = atomicAdd(sc.ticket + 1, 1u);
+          if (chunk >= totalChunks) { chunk = kNoChunk; chunksLeft = false; }
+        }
+        if (chunk != kNoChunk) {
+          while (__ldg(&sc.workIdx[chunkMember + 1].y) <= chunk) ++chunkMember;  // claims only grow
+          if (ldAcquire(sc.ready + chunkMember) != 0u) { act = kActEncode; arg = chunk; m = chunkMember; chunk = kNoChunk; }
+        }
+        if (act == kActWait && statsLeft) {
+          item = atomicAdd(sc.ticket + 0, 1u);
+          if (item >= totalItems) { statsLeft = false; item = 0xffffffffu; }
+        }
+        if (act == kActWait && item == 0xffffffffu && chunk == kNoChunk) act = kActExit;  // nothing left anywhere
+      }
+      if (item != 0xffffffffu) {
+        while (__ldg(&sc.workIdx[itemMember + 1].x) <= item) ++itemMember;
+        act = kActStats; arg = item; m = itemMember;
+      }
+      sCtl[0] = act; sCtl[1] = arg; sCtl[2] = m;
+    }
+    __syncthreads();
+    const uint32_t act = sCtl[0], arg = sCtl[1], m = sCtl[2];
+    if (act == kActExit) break;
+    if (act == kActStats) {
+      const uint2 w0 = __ldg(&sc.workIdx[m]), w1 = __ldg(&sc.workIdx[m + 1]);
+      bool finished;
+      if (KIND == kKindBytes) {
+        finished = statsBytesItem(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, m, arg - w0.x, w1.x - w0.x, outSize);
+      } else {
+        finished = statsFloatItem<KIND == kKindBytes ? DGB_FLOAT16 : KIND>(sc, sHist, pb, useChecksum, slabVecs, m,
+                                                                            arg - w0.x, w1.x - w0.x, outSize);
+      }
+      if (finished) {
+        // table, pdf and (through the ticket chain) every comp / stored byte of the member are
+        // visible before the flag
+        __threadfence();
+        __syncthreads();
+        if (t == 0) stRelease(sc.ready + m, 1u);
+      }
+    } else if (act == kActEncode) {
+      const MemberDesc md = sc.members[m];
+      if (tabMember != m) {
+        loadTable<WIDE>(sc, sTab, m);
+        tabMember = m;
+        __syncthreads();
+      }
+      const uint32_t nb = divUp(md.size, kBlockBytes);
+      const uint32_t first = (arg - __ldg(&sc.workIdx[m].y)) * chunkBlocks;
+      encodeMemberBlocks<WIDE>(sc, md, m, first, min(nb, first + chunkBlocks), KIND, pb, useChecksum, tabAddr, ws,
+                               warp, W, lane, outSize);
+    } else {
+      __nanosleep(256);
+    }
+    __syncthreads();  // sCtl, the table slot and the dynamic region are reused by the next step
+  }
+}
+
+size_t alignUp256(size_t v) { return (v + 255) & ~size_t(255); }
 
 int smCount() {
   // per device (a process may drive several); racing first calls write the same value
@@ -1063,7 +1263,109 @@ int smCount() {
   return cached[dev];
 }
 
+struct ScratchPlan {
+  size_t members, workIdx, uploadEnd, zeroBegin, hist, histDone, checksum, ticket, allocDone, ready, zeroEnd, lookback,
+      lookbackEnd, table, spill, compRows, total;
+  uint32_t compStride, spillWarps;
+};
+
+// Encoder warps that may need a spill slot (one slot = the worst-case stream of one block): never
+// more than the device can hold resident (64 warps per SM), never more than the batch has work
+// for, so small batches get small scratch (the reference's scratch scales with the batch too).
+uint32_t spillWarpBound(uint32_t n, uint64_t totalBlocks) {
+  const uint64_t resident = 64ull * (uint64_t)smCount();
+  const uint64_t work = 8ull * ((uint64_t)n * 2ull + totalBlocks);  // 8 warps per CTA, <= items + chunks CTAs
+  return (uint32_t)std::min(resident, work);
+}
+
+ScratchPlan planScratch(int kind, uint32_t n, uint32_t maxSize, uint32_t totalTickets, uint32_t spillWarps) {
+  ScratchPlan p{};
+  size_t o = 0;
+  // uploaded in one copy: member descriptors, then the fused launch's work index
+  p.members = o; o += sizeof(MemberDesc) * (size_t)n;
+  o = (o + 15) & ~size_t(15);
+  p.workIdx = o; o += sizeof(uint2) * ((size_t)n + 1);
+  p.uploadEnd = o;
+  o = alignUp256(o);
+  p.zeroBegin = o;
+  p.hist = o; o = alignUp256(o + sizeof(uint32_t) * kNumSymbols * (size_t)n);
+  p.histDone = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
+  p.checksum = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
+  p.ticket = o; o = alignUp256(o + 16);
+  p.allocDone = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)n);
+  p.ready = o; o = alignUp256(o + sizeof(uint32_t) * (size_t)n);
+  p.zeroEnd = o;
+  // look-back descriptors: canonical (ordered) layout only; cleared only then
+  p.lookback = o; o = alignUp256(o + sizeof(unsigned long long) * (size_t)totalTickets);
+  p.lookbackEnd = o;
+  p.table = o; o = alignUp256(o + sizeof(uint4) * kNumSymbols * (size_t)n);
+  p.spillWarps = spillWarps;
+  p.spill = o; o = alignUp256(o + (size_t)spillWarps * maxBlockWords(11) * 2u);
+  p.compStride = kind == kKindBytes ? 0u : roundUp(maxSize, 16u);
+  p.compRows = o; o = alignUp256(o + (size_t)p.compStride * n);
+  p.total = o;
+  return p;
+}
+
 uint32_t ticketsFor(uint32_t size) { return divUp(size, kBlockBytes); }
+
+// Joins the internal streams on every exit path: the caller frees / reuses its scratch when the
+// call returns, so work already queued on a helper stream must be ordered before whatever the
+// caller enqueues next on its own stream -- also when a later launch of the same call failed.
+struct ForkGuard {
+  StreamPool* pool = nullptr;
+  cudaStream_t stream = nullptr;
+  bool forked[kMaxParts] = {};
+  ~ForkGuard() {
+    if (!pool) return;
+    for (int k = 0; k < kMaxParts; ++k) {
+      if (!forked[k]) continue;
+      if (cudaEventRecord(pool->done[k], pool->s[k]) == cudaSuccess) cudaStreamWaitEvent(stream, pool->done[k], 0);
+    }
+  }
+};
+
+// per-thread reusable host staging (no allocation on the steady-state call path)
+struct HostStage {
+  std::vector<uint8_t> upload;
+  std::vector<uint64_t> weight;
+};
+HostStage& hostStage() {
+  static thread_local HostStage h;
+  return h;
+}
+
+template <int KIND, bool WIDE>
+int launchFused(const EncodeScratch& sc, const uint32_t* histogram_dev, int pb, bool checksum, uint32_t n,
+                uint32_t totalItems, uint32_t totalChunks, uint32_t slabVecs, uint32_t chunkBlocks,
+                uint32_t slotWords, uint32_t statsEvery, uint32_t spillWarps, uint32_t* outSize_dev,
+                cudaStream_t stream) {
+  auto kern = encodeFusedKernel<KIND, WIDE>;
+  constexpr uint32_t W = kStatsThreads / 32;
+  const size_t smemBytes = (size_t)W * encFastWarpSmem(slotWords);
+  static thread_local int perSm = 0;
+  static thread_local size_t perSmKey = 0;
+  int devOrdinal = 0;
+  DGB_CUDA_TRY(cudaGetDevice(&devOrdinal));
+  const size_t occKey = smemBytes | ((size_t)(devOrdinal + 1) << 40);
+  if (perSm == 0 || perSmKey != occKey) {
+    DGB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    int occ = 0;
+    DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)kStatsThreads, smemBytes));
+    perSm = std::max(occ, 1);
+    perSmKey = occKey;
+  }
+  uint64_t grid = (uint64_t)perSm * (uint64_t)smCount();
+  grid = std::min<uint64_t>(grid, (uint64_t)totalItems + totalChunks);
+  grid = std::min<uint64_t>(grid, spillWarps / W);  // every warp owns a spill slot
+  grid = std::max<uint64_t>(grid, 1);
+  timerBegin(kSlotFused, stream);
+  kern<<<(uint32_t)grid, kStatsThreads, smemBytes, stream>>>(sc, histogram_dev, pb, checksum, n, totalItems, totalChunks,
+                                                             slabVecs, chunkBlocks, slotWords, statsEvery, outSize_dev);
+  DGB_CUDA_TRY(cudaGetLastError());
+  timerEnd(kSlotFused, stream);
+  return DGB_OK;
+}
 
 }  // namespace
 
@@ -1071,7 +1373,7 @@ size_t encodeTempBytes(int kind, uint32_t n, uint32_t maxSize) {
   // worst case over warps-per-CTA choices: tickets with W = 1
   const uint64_t tickets = (uint64_t)n * divUp(maxSize, kBlockBytes);
   if (tickets > 0xffffffffull) return ~size_t(0);
-  return planScratch(kind, n, maxSize, (uint32_t)tickets).total + 256;
+  return planScratch(kind, n, maxSize, (uint32_t)tickets, spillWarpBound(n, tickets)).total + 256;
 }
 
 int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, uint32_t n,
@@ -1080,77 +1382,120 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   if (n == 0) return DGB_OK;
   if (pb < 9 || pb > 11) return DGB_ERR_INVALID_ARG;
   if (kind != kKindBytes && histogram_dev) return DGB_ERR_INVALID_ARG;
-  const Options& opt = options();
-  const uint32_t W = (uint32_t)std::max(1, std::min(opt.encode_warps, 8));  // warps per CTA
+  const Options opt = options();  // one snapshot per call
+  const uint32_t W = (uint32_t)std::max(1, std::min(opt.encode_warps, 8));  // warps per CTA (two-kernel path)
+  const uint32_t elemBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
+  const bool canonical = opt.encode_canonical != 0;
+  const bool fused = !canonical && opt.encode_fused != 0;
+  const uint32_t slabVecs = (uint32_t)std::max(1, opt.hist_slab_kb) * 1024u / 16u;
+  const uint32_t chunkBlocks = (uint32_t)std::max(1, std::min(opt.fused_chunk_blocks, 4096));
+  const bool doPass = histogram_dev == nullptr || checksum;
 
-  std::vector<MemberDesc> desc(n);
+  // ---- member table + work index (host staging, one upload) ----
+  HostStage& hs = hostStage();
+  const size_t descBytes = sizeof(MemberDesc) * (size_t)n;
+  const size_t idxOff = (descBytes + 15) & ~size_t(15);
+  hs.upload.resize(idxOff + sizeof(uint2) * ((size_t)n + 1));
+  MemberDesc* desc = reinterpret_cast<MemberDesc*>(hs.upload.data());
+  uint2* workIdx = reinterpret_cast<uint2*>(hs.upload.data() + idxOff);
   uint32_t maxSize = 0;
-  uint64_t tickets = 0;
+  uint64_t tickets = 0, items = 0, chunks = 0;
   for (uint32_t i = 0; i < n; ++i) {
     const HostMember& hm = members[i];
     if ((hm.size && !hm.in) || !hm.out) return DGB_ERR_INVALID_ARG;
     if (reinterpret_cast<uintptr_t>(hm.out) & 15u) return DGB_ERR_INVALID_ARG;
-    const uint32_t wordBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
-    if (reinterpret_cast<uintptr_t>(hm.in) & (wordBytes - 1u)) return DGB_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(hm.in) & (elemBytes - 1u)) return DGB_ERR_INVALID_ARG;
+    // the reference refuses members whose worst-case archive does not fit 32 bits
+    // (ans/GpuANSEncode.cu:13-25 CHECK_LE(rawSize, INT32_MAX)): the caller cannot have sized `out`
+    if ((kind == kKindBytes ? dgb_ans_max_compressed_size(hm.size) : dgb_float_max_compressed_size(kind, hm.size)) == 0u)
+      return DGB_ERR_TOO_LARGE;
     desc[i].in = hm.in;
     desc[i].out = hm.out;
     desc[i].size = hm.size;
     desc[i].work0 = (uint32_t)tickets;
-    tickets += ticketsFor(hm.size);
+    workIdx[i] = make_uint2((uint32_t)items, (uint32_t)chunks);
+    const uint32_t nb = ticketsFor(hm.size);
+    tickets += nb;
+    chunks += divUp(nb, chunkBlocks);
+    const uint32_t slabs = kind == kKindBytes ? bytesSlabs(hm.in, hm.size, slabVecs, doPass)
+                                              : floatSlabs(hm.in, hm.size, elemBytes, slabVecs);
+    items += std::max(1u, slabs);
     maxSize = std::max(maxSize, hm.size);
-    if (tickets > 0x7fffffffull) return DGB_ERR_TOO_LARGE;
+    if (tickets > 0x7fffffffull || items > 0x7fffffffull) return DGB_ERR_TOO_LARGE;
   }
+  workIdx[n] = make_uint2((uint32_t)items, (uint32_t)chunks);
   const uint32_t totalTickets = (uint32_t)tickets;
-  const ScratchPlan sp = planScratch(kind, n, maxSize, totalTickets);
+  const ScratchPlan sp = planScratch(kind, n, maxSize, totalTickets, spillWarpBound(n, tickets));
   if (!temp || tempBytes < sp.total || (reinterpret_cast<uintptr_t>(temp) & 255u))
     return temp && tempBytes >= sp.total ? DGB_ERR_INVALID_ARG : DGB_ERR_TEMP_TOO_SMALL;
 
   uint8_t* base = static_cast<uint8_t*>(temp);
   EncodeScratch sc;
   sc.members = reinterpret_cast<MemberDesc*>(base + sp.members);
+  sc.workIdx = reinterpret_cast<const uint2*>(base + sp.workIdx);
   sc.hist = reinterpret_cast<uint32_t*>(base + sp.hist);
   sc.histDone = reinterpret_cast<uint32_t*>(base + sp.histDone);
   sc.checksum = reinterpret_cast<uint32_t*>(base + sp.checksum);
   sc.ticket = reinterpret_cast<uint32_t*>(base + sp.ticket);
   sc.lookback = reinterpret_cast<unsigned long long*>(base + sp.lookback);
   sc.allocDone = reinterpret_cast<unsigned long long*>(base + sp.allocDone);
+  sc.ready = reinterpret_cast<uint32_t*>(base + sp.ready);
   sc.spill = base + sp.spill;
   sc.table = reinterpret_cast<uint4*>(base + sp.table);
   sc.compRows = base + sp.compRows;
   sc.compStride = sp.compStride;
 
-  DGB_CUDA_TRY(cudaMemcpyAsync(sc.members, desc.data(), sizeof(MemberDesc) * n,
-                               cudaMemcpyHostToDevice, stream));
-  DGB_CUDA_TRY(cudaMemsetAsync(base + sp.zeroBegin, 0, sp.zeroEnd - sp.zeroBegin, stream));
+  DGB_CUDA_TRY(cudaMemcpyAsync(base + sp.members, hs.upload.data(), hs.upload.size(), cudaMemcpyHostToDevice, stream));
+  DGB_CUDA_TRY(cudaMemsetAsync(base + sp.zeroBegin, 0, (canonical ? sp.lookbackEnd : sp.zeroEnd) - sp.zeroBegin, stream));
 
   const int sms = smCount();
-  const uint32_t elemBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
-  const bool canonical = opt.encode_canonical != 0;
   // encoder table format (see EncSym in this file): wide entries for exponent-byte planes
   const bool wideTable = !canonical && opt.encode_wide_table != 0 &&
                          (opt.encode_wide_table > 0 || kind == DGB_BFLOAT16 || kind == DGB_FLOAT32);
   sc.wideTable = wideTable;
 
-  // ---- sub-batches on internal streams (the ordered canonical encoder stays on one stream) ----
-  std::vector<uint64_t> weight(n);
+  // staging slot of the fast / fused encoder (spills to global scratch when a block needs more)
+  uint32_t slotWords = opt.encode_slot_words > 0 ? (uint32_t)opt.encode_slot_words
+                                                 : (kind == kKindBytes ? 2304u : 1536u);
+  slotWords = std::max<uint32_t>(roundUp(slotWords, 8u), kEncGroupRows * 32u + 264u);
+  slotWords = std::min(slotWords, maxBlockWords(pb));
+
+  if (fused) {
+    // ---- one persistent launch: statistics items and encode chunks from two counters ----
+    const uint32_t statsEvery = (uint32_t)std::max(0, opt.fused_stats_every);
+    const uint32_t ti = (uint32_t)items, tc = (uint32_t)chunks;
+#define DGB_FUSED(K, WD) \
+  launchFused<K, WD>(sc, histogram_dev, pb, checksum, n, ti, tc, slabVecs, chunkBlocks, slotWords, statsEvery, \
+                     sp.spillWarps, outSize_dev, stream)
+    switch (kind) {
+      case kKindBytes: return wideTable ? DGB_FUSED(kKindBytes, true) : DGB_FUSED(kKindBytes, false);
+      case kKindF16: return wideTable ? DGB_FUSED(kKindF16, true) : DGB_FUSED(kKindF16, false);
+      case kKindBF16: return wideTable ? DGB_FUSED(kKindBF16, true) : DGB_FUSED(kKindBF16, false);
+      case kKindF32: return wideTable ? DGB_FUSED(kKindF32, true) : DGB_FUSED(kKindF32, false);
+      default: return DGB_ERR_INVALID_ARG;
+    }
+#undef DGB_FUSED
+  }
+
+  // ---- two-kernel path: sub-batches on internal streams (the ordered canonical encoder stays on one) ----
+  hs.weight.resize(n);
   uint64_t totalBytes = 0;
-  for (uint32_t i = 0; i < n; ++i) { weight[i] = (uint64_t)desc[i].size * elemBytes; totalBytes += weight[i]; }
+  for (uint32_t i = 0; i < n; ++i) { hs.weight[i] = (uint64_t)desc[i].size * elemBytes; totalBytes += hs.weight[i]; }
   // byte inputs measured slightly slower when split (their stats kernel is atomics-bound, not HBM-bound)
   const int parts = canonical ? 1 : autoParts(kind, n, totalBytes, false);
   uint32_t bounds[kMaxParts + 1];
-  splitParts(weight.data(), n, parts, bounds);
+  splitParts(hs.weight.data(), n, parts, bounds);
+  ForkGuard guard;
   StreamPool* pool = nullptr;
   if (parts > 1) {
     int rc = streamPool(&pool);
     if (rc != DGB_OK) return rc;
     DGB_CUDA_TRY(cudaEventRecord(pool->start, stream));
+    guard.pool = pool;
+    guard.stream = stream;
   }
 
   // K2 launch configuration (same for every part)
-  uint32_t slotWords = opt.encode_slot_words > 0 ? (uint32_t)opt.encode_slot_words
-                                                 : (kind == kKindBytes ? 2304u : 1536u);
-  slotWords = std::max<uint32_t>(roundUp(slotWords, 8u), kEncGroupRows * 32u + 264u);
-  slotWords = std::min(slotWords, maxBlockWords(pb));
   const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb) : encFastWarpSmem(slotWords));
   // launch attributes and occupancy: cached per host thread, re-done when the kernel variant, its
   // shared-memory size or the thread's current device changes (function attributes are per device)
@@ -1185,7 +1530,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     occKeyDev = devOrdinal;
   }
   const uint64_t resident = (uint64_t)perSm * sms;
-  const uint32_t spillWarpsPerPart = kMaxSpillWarps / (uint32_t)parts;
+  const uint32_t spillWarpsPerPart = sp.spillWarps / (uint32_t)parts;
 
   for (int part = 0; part < parts; ++part) {
     const uint32_t m0 = bounds[part], m1 = bounds[part + 1];
@@ -1194,11 +1539,11 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     if (parts > 1) {
       ps = pool->s[part];
       DGB_CUDA_TRY(cudaStreamWaitEvent(ps, pool->start, 0));
+      guard.forked[part] = true;
     }
     // ---- K1 ----
     uint32_t partMax = 0;
     for (uint32_t i = m0; i < m1; ++i) partMax = std::max(partMax, desc[i].size);
-    const uint32_t slabVecs = std::max(1, opt.hist_slab_kb) * 1024u / 16u;
     const uint64_t maxVecs = ((uint64_t)partMax * elemBytes) / 16u;
     uint32_t gridY = (uint32_t)std::max<uint64_t>(1, (maxVecs + slabVecs - 1) / slabVecs);
     // enough CTAs to fill the machine a few times, never more than the slabs
@@ -1244,12 +1589,8 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
       DGB_CUDA_TRY(cudaGetLastError());
       timerEnd(kSlotEncode, ps);
     }
-    if (parts > 1) {
-      DGB_CUDA_TRY(cudaEventRecord(pool->done[part], ps));
-      DGB_CUDA_TRY(cudaStreamWaitEvent(stream, pool->done[part], 0));
-    }
   }
-  return DGB_OK;
+  return DGB_OK;  // ~ForkGuard joins the helper streams
 }
 
 }  // namespace dgb

@@ -187,7 +187,7 @@ int dgb_set_option(const char* name, int value);
 int dgb_get_option(const char* name, int* value);
 /* With option "timing" = 1 every kernel launch is bracketed by CUDA events on the caller's
  * stream; this returns (and resets) the summed durations in ms and launch counts per kernel:
- * slot 0 stats (K1), 1 encode (K2), 2 plan, 3 decode, 4 checksum.  Synchronises the device. */
+ * slot 0 stats (K1), 1 encode (K2), 2 plan, 3 decode, 4 checksum, 5 fused encode.  Synchronises the device. */
 int dgb_kernel_times(float* ms, int* counts, int nslots);
 
 #ifdef __cplusplus

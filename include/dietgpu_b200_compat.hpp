@@ -42,88 +42,214 @@ inline void check(const char* what, int code) {
 }
 }  // namespace detail
 
-// utils/StackDeviceMemory.h: caller-provided scratch with an allocation fallback.  Only what the
-// codec API needs is reproduced: construction, usage high-water mark, and (internally) one
-// reservation per call.  When the region is too small the call allocates a temporary region with
-// cudaMalloc, warns on stderr and frees it after synchronising the stream -- the behaviour of
-// utils/StackDeviceMemory.cpp:119-139.
-class StackDeviceMemory {
- public:
-  StackDeviceMemory(int device, size_t allocPerDevice) : device_(device), owned_(true), size_(allocPerDevice) {
-    int prev = 0;
-    cudaGetDevice(&prev);
-    cudaSetDevice(device);
-    if (cudaMalloc(&base_, allocPerDevice) != cudaSuccess) detail::fail("StackDeviceMemory cudaMalloc", DGB_ERR_CUDA);
-    cudaSetDevice(prev);
-  }
-  StackDeviceMemory(int device, void* p, size_t size) : device_(device), owned_(false), base_(p), size_(size) {}
-  StackDeviceMemory(const StackDeviceMemory&) = delete;
-  StackDeviceMemory& operator=(const StackDeviceMemory&) = delete;
-  StackDeviceMemory(StackDeviceMemory&& o) noexcept { *this = std::move(o); }
-  StackDeviceMemory& operator=(StackDeviceMemory&& o) noexcept {
-    std::swap(device_, o.device_); std::swap(owned_, o.owned_); std::swap(base_, o.base_);
-    std::swap(size_, o.size_); std::swap(maxUsed_, o.maxUsed_);
+// ---- utils/StackDeviceMemory.h:17-299 ----------------------------------------------------------
+// The scratch arena every API call takes as its first argument: a LIFO bump allocator over one
+// device region (owned or caller-provided), 256 B granularity, with the reference's overflow
+// behaviour -- a Temporary request that does not fit, and every Permanent request, is served by
+// cudaMalloc (Temporary overflows warn on stderr) and freed on release
+// (utils/StackDeviceMemory.cpp:105-184).  Temporary reservations must be released in reverse
+// order (:181); GpuMemoryReservation<T> does that on destruction.
+constexpr size_t kDefaultStackSize = 256 * 1024 * 1024;  // utils/StackDeviceMemory.h:19
+constexpr size_t kSDMAlignment = 256;                    // utils/StackDeviceMemory.h:24
+
+enum class AllocType { Temporary, Permanent };
+
+class StackDeviceMemory;
+
+template <typename T>
+struct GpuMemoryReservation {
+  GpuMemoryReservation() = default;
+  GpuMemoryReservation(StackDeviceMemory* r, int dev, cudaStream_t str, void* p, size_t n, size_t szAlloc)
+      : res(r), device(dev), stream(str), ptr(p), num(n), sizeAllocated(szAlloc) {}
+  GpuMemoryReservation(const GpuMemoryReservation&) = delete;
+  GpuMemoryReservation& operator=(const GpuMemoryReservation&) = delete;
+  GpuMemoryReservation(GpuMemoryReservation&& m) noexcept { take(m); }
+  GpuMemoryReservation& operator=(GpuMemoryReservation&& m) {
+    if (this != &m) {
+      release();
+      take(m);
+    }
     return *this;
   }
-  ~StackDeviceMemory() { if (owned_ && base_) cudaFree(base_); }
+  ~GpuMemoryReservation() { release(); }
+
+  T* data() { return static_cast<T*>(ptr); }
+  const T* data() const { return static_cast<const T*>(ptr); }
+
+  // device -> host std::vector<T>, ordered after `onStream` (pageable destination: the copy has
+  // completed when this returns, which is what the reference's tests rely on)
+  std::vector<T> copyToHost(cudaStream_t onStream) const {
+    std::vector<T> out(num);
+    if (num && cudaMemcpyAsync(out.data(), ptr, num * sizeof(T), cudaMemcpyDeviceToHost, onStream) != cudaSuccess)
+      detail::fail("GpuMemoryReservation::copyToHost", DGB_ERR_CUDA);
+    return out;
+  }
+
+  inline void release();
+
+  StackDeviceMemory* res = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  void* ptr = nullptr;
+  size_t num = 0;            // valid elements of T
+  size_t sizeAllocated = 0;  // bytes taken from the arena
+
+ private:
+  void take(GpuMemoryReservation& m) {
+    res = m.res; device = m.device; stream = m.stream; ptr = m.ptr; num = m.num; sizeAllocated = m.sizeAllocated;
+    m.res = nullptr; m.ptr = nullptr; m.num = 0; m.sizeAllocated = 0;
+  }
+};
+
+class StackDeviceMemory {
+ public:
+  StackDeviceMemory(int device, size_t allocPerDevice) : device_(device) {
+    if (allocPerDevice) {
+      int prev = 0;
+      cudaGetDevice(&prev);
+      cudaSetDevice(device);
+      const size_t bytes = (allocPerDevice + kSDMAlignment - 1) / kSDMAlignment * kSDMAlignment;
+      if (cudaMalloc(&owned_, bytes) != cudaSuccess) detail::fail("StackDeviceMemory cudaMalloc", DGB_ERR_CUDA);
+      cudaSetDevice(prev);
+      setRegion(owned_, bytes);
+    }
+  }
+  StackDeviceMemory(int device, void* p, size_t size) : device_(device) { setRegion(p, p ? size : 0); }
+  StackDeviceMemory(const StackDeviceMemory&) = delete;
+  StackDeviceMemory& operator=(const StackDeviceMemory&) = delete;
+  // movable only while no reservation is outstanding (reservations point back at the arena)
+  StackDeviceMemory(StackDeviceMemory&& o) noexcept { swap(o); }
+  StackDeviceMemory& operator=(StackDeviceMemory&& o) noexcept {
+    swap(o);
+    return *this;
+  }
+  ~StackDeviceMemory() {
+    for (auto& ov : overflow_) cudaFree(ov.first);
+    if (owned_) cudaFree(owned_);
+  }
 
   int getDevice() const { return device_; }
-  size_t getSizeAvailable() const { return alignedSize(); }
-  size_t getSizeTotal() const { return size_; }
-  size_t getMaxMemoryUsage() const { return maxUsed_; }
-  void resetMaxMemoryUsage() { maxUsed_ = 0; }
 
-  // One scratch region for the duration of a call.
-  struct Lease {
-    void* ptr = nullptr;
-    size_t bytes = 0;
-    void* fallback = nullptr;
-    cudaStream_t stream = nullptr;
-    Lease() = default;
-    Lease(const Lease&) = delete;
-    Lease(Lease&& o) noexcept { std::swap(ptr, o.ptr); std::swap(bytes, o.bytes); std::swap(fallback, o.fallback); std::swap(stream, o.stream); }
-    ~Lease() {
-      if (fallback) {
+  template <typename T>
+  GpuMemoryReservation<T> alloc(cudaStream_t stream, size_t num, AllocType type = AllocType::Temporary) {
+    size_t bytes = (num * sizeof(T) + kSDMAlignment - 1) / kSDMAlignment * kSDMAlignment;
+    bytes = std::max(bytes, kSDMAlignment);
+    return GpuMemoryReservation<T>(this, device_, stream, allocPointer(stream, bytes, type), num, bytes);
+  }
+  // host (or device) array -> new reservation, copy ordered on `stream`
+  template <typename T>
+  GpuMemoryReservation<T> copyAlloc(cudaStream_t stream, const T* src, size_t num, AllocType type = AllocType::Temporary) {
+    auto mem = alloc<T>(stream, num, type);
+    if (num && cudaMemcpyAsync(mem.data(), src, num * sizeof(T), cudaMemcpyDefault, stream) != cudaSuccess)
+      detail::fail("StackDeviceMemory::copyAlloc", DGB_ERR_CUDA);
+    return mem;
+  }
+  template <typename T>
+  GpuMemoryReservation<T> copyAlloc(cudaStream_t stream, const std::vector<T>& v, AllocType type = AllocType::Temporary) {
+    return copyAlloc<T>(stream, v.data(), v.size(), type);
+  }
+
+  // size: a multiple of kSDMAlignment
+  void* allocPointer(cudaStream_t, size_t size, AllocType type) {
+    if (size == 0 || size % kSDMAlignment) detail::fail("StackDeviceMemory::allocPointer (size not 256 B granular)", DGB_ERR_INVALID_ARG);
+    void* out = nullptr;
+    const size_t used = (size_t)(head_ - start_);
+    if (type == AllocType::Permanent || size > getSizeAvailable()) {
+      if (type == AllocType::Temporary) {
+        std::fprintf(stderr,
+                     "dietgpu_b200 WARNING: StackDeviceMemory: %zu bytes requested with %zu available; calling "
+                     "cudaMalloc. Size the temporary memory to >= %zu bytes to avoid this.\n",
+                     size, getSizeAvailable(), std::max(maxSeen_, used + overflowBytes_ + size));
+      }
+      int prev = 0;
+      cudaGetDevice(&prev);
+      if (prev != device_) cudaSetDevice(device_);
+      if (cudaMalloc(&out, size) != cudaSuccess) detail::fail("StackDeviceMemory overflow cudaMalloc", DGB_ERR_CUDA);
+      if (prev != device_) cudaSetDevice(prev);
+      overflow_.emplace_back(out, size);
+      overflowBytes_ += size;
+    } else {
+      out = head_;
+      head_ += size;
+    }
+    maxSeen_ = std::max(maxSeen_, (size_t)(head_ - start_) + overflowBytes_);
+    return out;
+  }
+  void deallocPointer(int device, cudaStream_t stream, size_t size, void* p) {
+    if (!p || device != device_) detail::fail("StackDeviceMemory::deallocPointer", DGB_ERR_INVALID_ARG);
+    for (size_t i = 0; i < overflow_.size(); ++i) {
+      if (overflow_[i].first == p) {
+        // kernels that use the region may still be queued on the stream it was handed out for
         cudaStreamSynchronize(stream);
-        cudaFree(fallback);
+        cudaFree(p);
+        overflowBytes_ -= overflow_[i].second;
+        overflow_.erase(overflow_.begin() + (long)i);
+        return;
       }
     }
+    char* pc = static_cast<char*>(p);
+    // Temporary reservations are returned in reverse order (utils/StackDeviceMemory.cpp:181)
+    if (pc < start_ || pc + size != head_) detail::fail("StackDeviceMemory: reservations released out of order", DGB_ERR_INVALID_ARG);
+    head_ = pc;
+  }
+
+  size_t getSizeAvailable() const { return (size_t)(end_ - head_); }
+  size_t getSizeTotal() const { return (size_t)(end_ - start_); }
+  size_t getMaxMemoryUsage() const { return maxSeen_; }
+  void resetMaxMemoryUsage() { maxSeen_ = 0; }
+  std::string toString() const {
+    return "SDM device " + std::to_string(device_) + ": total " + std::to_string(getSizeTotal()) + " B, available " +
+           std::to_string(getSizeAvailable()) + " B, maximum seen usage " + std::to_string(maxSeen_) + " B\n";
+  }
+
+  // One scratch region for the duration of a codec call (the C ABI takes a plain pointer + size).
+  struct Lease {
+    GpuMemoryReservation<uint8_t> mem;
+    void* ptr = nullptr;
+    size_t bytes = 0;
   };
   Lease lease(size_t need, cudaStream_t stream) {
-    maxUsed_ = std::max(maxUsed_, need);
     Lease l;
-    l.stream = stream;
+    l.mem = alloc<uint8_t>(stream, std::max<size_t>(need, 1));
+    l.ptr = l.mem.data();
     l.bytes = need;
-    if (alignedSize() >= need) {
-      l.ptr = alignedBase();
-      return l;
-    }
-    std::fprintf(stderr,
-                 "dietgpu_b200 WARNING: temporary memory of %zu bytes requested, %zu available; "
-                 "falling back to cudaMalloc (synchronises the stream)\n", need, alignedSize());
-    if (cudaMalloc(&l.fallback, need) != cudaSuccess) detail::fail("temporary cudaMalloc", DGB_ERR_CUDA);
-    l.ptr = l.fallback;
     return l;
   }
 
  private:
-  void* alignedBase() const {
-    auto a = reinterpret_cast<uintptr_t>(base_);
-    return reinterpret_cast<void*>((a + 255) & ~uintptr_t(255));
+  void setRegion(void* p, size_t size) {
+    // allocations are handed out on 256 B boundaries whatever the caller's pointer is
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + kSDMAlignment - 1) & ~uintptr_t(kSDMAlignment - 1);
+    const size_t pad = (size_t)(a - reinterpret_cast<uintptr_t>(p));
+    start_ = head_ = reinterpret_cast<char*>(a);
+    end_ = start_ + (size > pad ? (size - pad) / kSDMAlignment * kSDMAlignment : 0);
   }
-  size_t alignedSize() const {
-    if (!base_) return 0;
-    size_t pad = reinterpret_cast<uintptr_t>(alignedBase()) - reinterpret_cast<uintptr_t>(base_);
-    return size_ > pad ? size_ - pad : 0;
+  void swap(StackDeviceMemory& o) {
+    std::swap(device_, o.device_); std::swap(owned_, o.owned_); std::swap(start_, o.start_);
+    std::swap(end_, o.end_); std::swap(head_, o.head_); std::swap(overflow_, o.overflow_);
+    std::swap(overflowBytes_, o.overflowBytes_); std::swap(maxSeen_, o.maxSeen_);
   }
   int device_ = 0;
-  bool owned_ = false;
-  void* base_ = nullptr;
-  size_t size_ = 0;
-  size_t maxUsed_ = 0;
+  void* owned_ = nullptr;
+  char* start_ = nullptr;
+  char* end_ = nullptr;
+  char* head_ = nullptr;
+  std::vector<std::pair<void*, size_t>> overflow_;
+  size_t overflowBytes_ = 0;
+  size_t maxSeen_ = 0;
 };
 
-inline StackDeviceMemory makeStackMemory(size_t bytes = 256 * 1024 * 1024) {
+template <typename T>
+inline void GpuMemoryReservation<T>::release() {
+  if (ptr && res) res->deallocPointer(device, stream, sizeAllocated, ptr);
+  res = nullptr;
+  ptr = nullptr;
+  num = 0;
+  sizeAllocated = 0;
+}
+
+// utils/StackDeviceMemory.h:297-299 / .cpp:248-250
+inline StackDeviceMemory makeStackMemory(size_t bytes = kDefaultStackSize) {
   int dev = 0;
   cudaGetDevice(&dev);
   return StackDeviceMemory(dev, bytes);

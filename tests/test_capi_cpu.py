@@ -53,8 +53,8 @@ def test_error_codes_without_gpu():
     assert L.dgb_float_compress_pointer(None, 0, 9, 10, 0, 1, one, sz, one, None, None) == capi.ERR_INVALID_ARG
     assert L.dgb_ans_encode_pointer(None, 0, 10, 0, 1, one, sz, None, one, None, None) == capi.ERR_TEMP_TOO_SMALL
     assert L.dgb_set_option(b"no_such_option", 1) == capi.ERR_INVALID_ARG
-    capi.set_option("decode_stage", 1)
-    assert capi.get_option("decode_stage") == 1
+    capi.set_option("decode_fused", 1)
+    assert capi.get_option("decode_fused") == 1
 
 
 def test_product_does_not_import_oracle():

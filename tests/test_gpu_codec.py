@@ -460,23 +460,35 @@ def test_encoder_table_formats():
 
 
 def test_kernel_variants_agree():
-    # every tuning variant produces identical results
+    # every tuning variant produces identical results: single-launch vs two-kernel paths in both
+    # directions, chunk sizes, statistics-CTA share, warps per CTA, canonical packing
     from dietgpu_b200 import capi
 
-    a = [zipf_bytes(300000, 1.1, 5), exp_bytes(4097, 50, 6)]
+    a = [zipf_bytes(300000, 1.1, 5), exp_bytes(4097, 50, 6), zipf_bytes(1, 1.0, 7), np.zeros(0, np.uint8)]
+    f = [normal_words(50000 + 13 * i, "bf16", i) for i in range(5)]
+    names = ("encode_fused", "decode_fused", "fused_chunk_blocks", "decode_chunk_blocks", "fused_stats_every",
+             "encode_warps", "encode_canonical")
+    defaults = {k: capi.get_option(k) for k in names}
+    variants = [
+        dict(encode_fused=0, decode_fused=0),
+        dict(encode_fused=1, decode_fused=0),
+        dict(encode_fused=0, decode_fused=1),
+        dict(fused_chunk_blocks=1, decode_chunk_blocks=1),
+        dict(fused_chunk_blocks=3, decode_chunk_blocks=5),
+        dict(fused_chunk_blocks=64, decode_chunk_blocks=64),
+        dict(fused_stats_every=0),
+        dict(fused_stats_every=1),
+        dict(encode_fused=0, encode_warps=2),
+        dict(encode_fused=0, encode_warps=4),
+        dict(encode_canonical=1),
+        dict(encode_canonical=1, decode_fused=0),
+    ]
     try:
-        for stage in (0, 1):
-            for dw in (4, 8):
-                for ew in (2, 4, 8):
-                    for l64 in (0, 1):
-                        for canon in (0, 1):
-                            capi.set_option("decode_stage", stage)
-                            capi.set_option("decode_warps", dw)
-                            capi.set_option("encode_warps", ew)
-                            capi.set_option("decode_lut64", l64)
-                            capi.set_option("encode_canonical", canon)
-                            ans_roundtrip(a, 10)
+        for v in variants:
+            for k, d in defaults.items():
+                capi.set_option(k, v.get(k, d))
+            ans_roundtrip(a, 10)
+            float_roundtrip("bf16", f, 10)
     finally:
-        for k, v in (("decode_stage", 1), ("decode_warps", 8), ("encode_warps", 8), ("decode_lut64", 0),
-                     ("encode_canonical", 0)):
-            capi.set_option(k, v)
+        for k, d in defaults.items():
+            capi.set_option(k, d)

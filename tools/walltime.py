@@ -14,13 +14,21 @@ kind, batch, per, desc = bench.WORKLOADS[wl]
 ts = bench.make_batch(torch, kind, batch, per, 1234, torch.device("cuda", 0))
 ub = sum(t.numel() * t.element_size() for t in ts)
 it = torch.int16 if kind != "bytes" else torch.uint8
+defaults = {}
+sizes0 = None
 for v in sys.argv[2:] or [""]:
+    for k, val in defaults.items():  # every variant starts from the defaults
+        capi.set_option(k, val)
     for kv in [x for x in v.split(",") if x]:
         k, val = kv.split("=")
+        defaults.setdefault(k, capi.get_option(k))
         capi.set_option(k, int(val))
     c = bench.OursCodec(torch, kind, ts)
     c.encode(); c.bind_rows(); c.decode(); torch.cuda.synchronize()
     ok = all(torch.equal(a.view(it), b.view(it)) for a, b in zip(ts, c.outs))
+    sz = c.sizes.cpu().tolist()
+    sizes0 = sizes0 or sz
+    ok = ok and sz == sizes0  # archive sizes do not depend on the kernel variant
     for _ in range(3):
         c.encode(); c.decode()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
