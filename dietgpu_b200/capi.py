@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdietgpu_b200.so")
+# DIETGPU_B200_LIB selects an experiment build of the same library (tools/ only); default = the shipped one
+LIB_PATH = os.environ.get("DIETGPU_B200_LIB") or os.path.join(_HERE, "libdietgpu_b200.so")
 
 OK, ERR_INVALID_ARG, ERR_TEMP_TOO_SMALL, ERR_CUDA, ERR_CHECKSUM, ERR_TOO_LARGE = range(6)
 FLOAT16, BFLOAT16, FLOAT32 = 1, 2, 3
@@ -26,6 +27,7 @@ SYMBOLS = [
     "dgb_float_compress_pointer", "dgb_float_compress_split_size",
     "dgb_float_decompress_pointer", "dgb_float_decompress_split_size",
     "dgb_float_get_compressed_info",
+    "dgb_copy_async", "dgb_copy_rows_async",
     "dgb_set_option", "dgb_get_option", "dgb_kernel_times",
 ]
 
@@ -94,6 +96,10 @@ def lib():
     L.dgb_set_option.argtypes = [C.c_char_p, i32]
     L.dgb_get_option.restype = i32
     L.dgb_get_option.argtypes = [C.c_char_p, C.POINTER(i32)]
+    L.dgb_copy_async.restype = i32
+    L.dgb_copy_async.argtypes = [vp, vp, sz, vp]
+    L.dgb_copy_rows_async.restype = i32
+    L.dgb_copy_rows_async.argtypes = [vp, sz, vp, sz, sz, sz, vp]
     L.dgb_kernel_times.restype = i32
     L.dgb_kernel_times.argtypes = [vp, vp, i32]
     _lib = L

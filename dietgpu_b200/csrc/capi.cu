@@ -79,11 +79,13 @@ int autoParts(int kind, uint32_t n, uint64_t totalBytes, bool decode) {
   const Options& o = options();
   if (o.timing) return 1;  // per-kernel timing wants un-overlapped launches
   int p = o.parts;
-  // measured on B200 (tools/walltime.py, 256 MiB batches): encode is best with 2 sub-batches (its two
-  // kernels overlap), decode with 4 (plan latency and kernel tails hide); byte inputs gain nothing
+  // measured on B200 (tools/walltime.py, 256 MiB batches): float encode is best with 4 sub-batches
+  // (the bandwidth-bound statistics kernel of one sub-batch runs beside the issue-bound coder of the
+  // previous one: c3 204 / 195 / 189 us for 1 / 2 / 4), the two-kernel decoder with 4 (plan latency
+  // and kernel tails hide); byte inputs gain nothing
   if (p <= 0) {
     const bool big = kind != kKindBytes && totalBytes >= (64ull << 20);
-    p = !big ? 1 : (decode ? (n >= 16 ? 4 : (n >= 8 ? 2 : 1)) : (n >= 8 ? 2 : 1));
+    p = !big ? 1 : (n >= 16 ? 4 : (n >= 8 ? 2 : 1));
   }
   p = std::min(p, kMaxParts);
   return (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)p, n));
@@ -147,7 +149,7 @@ uint32_t dgb_ans_max_compressed_size(uint32_t bytes) {
   // The reference CHECKs rawSize <= INT32_MAX (process abort); this ABI returns 0 = "too large"
   // instead of a wrapped value a caller would size its output buffer from.
   uint64_t raw = ansOverhead(kBlockBytes);
-  raw += (uint64_t)roundUp(kBlockBytes + kBlockBytes / 4u, 16u) * divUp(bytes, kBlockBytes);
+  raw += (uint64_t)roundUp(kBlockBytes + kBlockBytes / 4u, 16u) * (((uint64_t)bytes + kBlockBytes - 1) / kBlockBytes);
   raw = roundUp64(raw, 16);
   return raw <= 0x7fffffffull ? (uint32_t)raw : 0u;
 }
@@ -335,18 +337,35 @@ int dgb_float_get_compressed_info(void* temp, size_t tempBytes, const void* cons
                  outChecksum_dev, (cudaStream_t)stream);
 }
 
+// ---- host front end helpers ---------------------------------------------------
+int dgb_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return DGB_OK;
+  if (!dst || !src) return DGB_ERR_INVALID_ARG;
+  DGB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return DGB_OK;
+}
+
+int dgb_copy_rows_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                        size_t width_bytes, size_t rows, void* stream) {
+  if (width_bytes == 0 || rows == 0) return DGB_OK;
+  if (!dst || !src || width_bytes > dst_pitch || width_bytes > src_pitch) return DGB_ERR_INVALID_ARG;
+  DGB_CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault,
+                                 (cudaStream_t)stream));
+  return DGB_OK;
+}
+
 // ---- options ---------------------------------------------------------------
 
 static int* optionSlot(const char* name) {
   Options& o = options();
   if (!name) return nullptr;
   if (!std::strcmp(name, "decode_fused")) return &o.decode_fused;
-  if (!std::strcmp(name, "decode_chunk_blocks")) return &o.decode_chunk_blocks;
   if (!std::strcmp(name, "decode_slot_words")) return &o.decode_slot_words;
   if (!std::strcmp(name, "encode_warps")) return &o.encode_warps;
   if (!std::strcmp(name, "encode_canonical")) return &o.encode_canonical;
   if (!std::strcmp(name, "encode_fused")) return &o.encode_fused;
   if (!std::strcmp(name, "fused_stats_every")) return &o.fused_stats_every;
+  if (!std::strcmp(name, "fused_stage")) return &o.fused_stage;
   if (!std::strcmp(name, "fused_chunk_blocks")) return &o.fused_chunk_blocks;
   if (!std::strcmp(name, "encode_wide_table")) return &o.encode_wide_table;
   if (!std::strcmp(name, "encode_slot_words")) return &o.encode_slot_words;

@@ -71,13 +71,13 @@ struct __align__(16) EncEntryWide {
 
 // ---- tuning options (dgb_set_option) ---------------------------------------
 struct Options {
-  int decode_fused = 1;      // 1: one persistent launch with member-affine chunk claiming; 0: plan + decode kernels
-  int decode_chunk_blocks = 16;  // single-launch decoder: 4 KiB blocks per claimed chunk
+  int decode_fused = 1;      // 1: one persistent launch, CTAs lease members and warps claim blocks; 0: plan + decode kernels
   int decode_slot_words = 0; // TMA staging slot per warp in u16 words; 0 = auto
   int encode_warps = 8;      // warps per encode CTA (each warp is an independent worker)
   int encode_slot_words = 0; // staging slot of the fast encoder in u16 words; 0 = auto
   int encode_canonical = 0;  // 1: streams packed in block order (byte-identical archives, slower)
-  int encode_fused = 1;      // 1: one persistent launch (statistics items + encode chunks), 0: two kernels
+  int encode_fused = 0;      // 1: one persistent launch (statistics items + encode chunks), 0: two kernels (default: measured equal or faster)
+  int fused_stage = 1;       // fused launch: statistics slabs land in shared memory by TMA bulk copy (0: register loads)
   int fused_stats_every = 4; // fused launch: one CTA in this many prefers statistics items (0: none does)
   int fused_chunk_blocks = 16;  // fused launch: 4 KiB blocks per encode chunk
   int encode_wide_table = -1;  // encoder table entries: 1 = 16 B, 0 = 8 B, -1 = by data kind (bf16/fp32 wide)
@@ -115,7 +115,7 @@ enum TimerSlot : int { kSlotStats = 0, kSlotEncode = 1, kSlotPlan = 2, kSlotDeco
 // Internal helper streams: a large batch is cut into up to kMaxParts contiguous sub-batches whose
 // kernels run on separate streams (forked from / joined to the caller's stream with events), so the
 // HBM-bound and the issue-bound kernels of different sub-batches overlap and launch gaps hide.
-constexpr int kMaxParts = 4;
+constexpr int kMaxParts = 8;
 struct StreamPool {
   cudaStream_t s[kMaxParts];
   cudaEvent_t start, done[kMaxParts];

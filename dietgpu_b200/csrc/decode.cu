@@ -39,8 +39,9 @@ namespace {
 
 struct DecodeScratch {
   MemberDesc* members;   // [n]; two-kernel path: planKernel fills work0 = first flat block;
-                         //      single-launch path: work0 = the member's chunk count (host, from capacity)
-  uint32_t* next;        // [n] single-launch path: next unclaimed chunk of the member (zeroed)
+                         //      single-launch path: work0 = upper bound of the member's block count (host, from capacity)
+  uint32_t* next;        // [n] single-launch path: next unclaimed block of the member (zeroed)
+  uint32_t* seen;        // [n] single-launch path: 1 once a CTA has reported the member (zeroed)
   uint32_t* totals;      // [0] = total blocks, [1] = unused
   uint32_t* checksum;    // [n] checksum of decoded output (use_checksum only; zeroed)
   uint32_t* archiveChecksum;  // [n]
@@ -588,24 +589,25 @@ decodeKernel(DecodeScratch sc, uint32_t m0, uint32_t m1, uint32_t part, uint32_t
 }
 
 // ---------------------------------------------------------------------------
-// Single-launch decoder (default).  One persistent grid, no plan kernel, no sub-batches: the host
-// knows every member's capacity, so it cuts each member into chunks of `chunkBlocks` 4 KiB blocks
-// (work0 = chunk count, at least one so that every header is visited) and zeroes one claim counter
-// per member.  A CTA starts at its home member, claims chunks of that member with one atomic each
-// (the next claim is issued before the current chunk is decoded, so its latency hides), and moves
-// on to the next member that still has unclaimed chunks when its own runs out: the decode LUT is
-// rebuilt only on a member switch, and all CTAs finish within one chunk of each other (the static
-// split of the two-kernel path left SMs idle for ~15 % of the kernel, ncu r01).  The CTA that
-// claims chunk 0 of a member validates its header(s) and reports outSuccess / outSize
-// (ans/GpuANSDecode.cuh:326-341 semantics); chunks past the archive's real block count, or of a
-// member that failed, are claimed and dropped.
+// Single-launch decoder (default).  One persistent grid, no plan kernel, no sub-batches.  The host
+// knows every member's capacity, hence an upper bound on its 4 KiB block count (work0; at least one
+// so that every header is visited), and zeroes one claim counter per member.  A CTA LEASES a
+// member: it reads and validates the header(s), builds the decode LUT once, and then each of its
+// warps claims blocks of that member one at a time with an atomic (the next claim is issued before
+// the current block is decoded, so its latency hides) until none are left; only then do the warps
+// meet at a barrier and the CTA moves on to the next member that still has unclaimed blocks,
+// starting from its home member.  Several CTAs lease the same member at once, so the work balances
+// at block granularity and the kernel has no per-block or per-chunk CTA barrier (the static split
+// of the two-kernel path left SMs idle for ~15 % of the kernel, ncu r01).  The first CTA to lease a
+// member reports outSuccess / outSize (ans/GpuANSDecode.cuh:326-341 semantics); claims past the
+// archive's real block count, or of a member that failed, are dropped.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kNoMember = 0xffffffffu;
 
 template <int KIND, int PB, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, DGB_DECODE_WARPS_PER_SM / WARPS)
-decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t chunkBlocks, uint32_t slotWords,
-                  uint8_t* __restrict__ outSuccess, uint32_t* __restrict__ outSize, bool wantChecksum) {
+decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords, uint8_t* __restrict__ outSuccess,
+                  uint32_t* __restrict__ outSize, bool wantChecksum) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t K = 1u << PB;
   typedef typename Lut<PB, false>::Entry Entry;
@@ -629,38 +631,24 @@ decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t chunkBlocks, uint32_t s
   fenceBarrierInit();
   __syncthreads();
 
-  // claim state: lives in warp 0 (uniform there), broadcast through sMisc
-  uint32_t cursor = (uint32_t)((uint64_t)blockIdx.x * n / gridDim.x);  // home member
-  uint32_t pending = kNoMember, pendingChunk = 0;  // a claim issued ahead of time (lane 0 of warp 0)
-  uint32_t lutMember = kNoMember;
-  bool memberOk = false;
-  uint32_t nb = 0;
-  ArchiveView av;
-  av.ok = false;
-  av.ans = nullptr; av.non = nullptr; av.floatWords = 0;
+  uint32_t cursor = (uint32_t)((uint64_t)blockIdx.x * n / gridDim.x);  // home member (used by warp 0)
 
   for (;;) {
+    // ---- lease: the first member at or after the cursor of which this CTA can still claim a block
+    //      (the claim comes first: a CTA that arrives when others have just taken the last blocks
+    //      moves on without reading the header or building the LUT) ----
     if (warp == 0) {
-      uint32_t cm = kNoMember, cc = 0;
-      if (pending != kNoMember) {
-        // the claim made before the previous chunk was decoded
-        const uint32_t c = __shfl_sync(0xffffffffu, pendingChunk, 0);
-        if (c < __ldg(&sc.members[pending].work0)) { cm = pending; cc = c; }
-        else cursor = pending + 1 == n ? 0u : pending + 1;
-        pending = kNoMember;
-      }
-      uint32_t tries = 0;
-      while (cm == kNoMember && tries < n) {
-        // 32 members at a time: who still has unclaimed chunks?
+      uint32_t pick = kNoMember, firstBlock = 0, tries = 0;
+      while (tries < n) {
+        // 32 members at a time
         uint32_t mm = cursor + lane;
         if (mm >= n) mm -= n;
-        const bool inRange = tries + lane < n;
         bool has = false;
-        if (inRange) has = *reinterpret_cast<volatile uint32_t*>(sc.next + mm) < __ldg(&sc.members[mm].work0);
+        if (tries + lane < n) has = *reinterpret_cast<volatile uint32_t*>(sc.next + mm) < __ldg(&sc.members[mm].work0);
         const uint32_t mask = __ballot_sync(0xffffffffu, has);
         if (mask == 0u) {
           tries += 32u;
-          cursor = cursor + 32u >= n ? (cursor + 32u) % n : cursor + 32u;
+          cursor = (cursor + 32u) % n;
           continue;
         }
         const uint32_t first = (uint32_t)__ffs((int)mask) - 1u;
@@ -669,59 +657,67 @@ decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t chunkBlocks, uint32_t s
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(sc.next + cand, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
-        if (c < __ldg(&sc.members[cand].work0)) { cm = cand; cc = c; cursor = cand; }
-        else { tries += first + 1u; cursor = cand + 1 == n ? 0u : cand + 1; }  // lost the race for its last chunk
+        if (c < __ldg(&sc.members[cand].work0)) {
+          pick = cand;
+          firstBlock = c;
+          cursor = cand;
+          break;
+        }
+        tries += first + 1u;  // lost the race for its last block
+        cursor = cand + 1 == n ? 0u : cand + 1;
       }
-      if (cm != kNoMember) {
-        // next claim of the same member, in flight while this chunk is decoded
-        pending = cm;
-        if (lane == 0) pendingChunk = atomicAdd(sc.next + cm, 1u);
-      }
-      if (lane == 0) { sMisc[0] = cm; sMisc[1] = cc; }
+      if (lane == 0) { sMisc[0] = pick; sMisc[1] = firstBlock; }
     }
     __syncthreads();
-    const uint32_t m = sMisc[0], chunk = sMisc[1];
+    const uint32_t m = sMisc[0];
     if (m == kNoMember) break;
     const MemberDesc md = sc.members[m];
-    if (lutMember != m || chunk == 0u) {
-      // ---- member switch: header(s), validity, LUT ----
-      av = openArchive<KIND>(static_cast<const uint8_t*>(md.in));
-      bool ok = av.ok;
-      uint32_t need = 0, storedChecksum = 0;
-      nb = 0;
-      if (ok) {
-        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(av.ans));
-        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(av.ans) + 1);
-        nb = h0.y;
-        need = h0.z;  // uncompressed bytes == float words for float kinds
-        ok = h0.x == kAnsMagicVersion && (int)(h1.x & 0xfu) == PB && nb == divUp(need, kBlockBytes);
-        if (KIND != kKindBytes) ok = ok && need == av.floatWords;
-        storedChecksum = KIND == kKindBytes ? h1.y : __ldg(reinterpret_cast<const uint32_t*>(md.in) + 3);
-      }
-      // ans/GpuANSDecode.cuh:326-337: success iff capacity suffices; size reported regardless
-      memberOk = ok && md.size >= need;
-      if (chunk == 0u && t == 0) {
-        if (outSuccess) outSuccess[m] = memberOk ? 1 : 0;
-        if (outSize) outSize[m] = ok ? need : 0u;
-        if (wantChecksum) {
-          sc.archiveChecksum[m] = storedChecksum;
-          sc.sizes[m] = memberOk ? need : 0u;
-        }
-      }
-      if (memberOk && nb > 0 && lutMember != m) buildLut<PB, false, WARPS>(av.ans, lut, sPdf, sCdf, sWarp);
-      lutMember = memberOk && nb > 0 ? m : kNoMember;
+    const uint32_t blocksCap = md.work0;
+
+    // ---- header(s), validity, LUT ----
+    const ArchiveView av = openArchive<KIND>(static_cast<const uint8_t*>(md.in));
+    bool ok = av.ok;
+    uint32_t need = 0, storedChecksum = 0, nb = 0;
+    if (ok) {
+      const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(av.ans));
+      const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(av.ans) + 1);
+      nb = h0.y;
+      need = h0.z;  // uncompressed bytes == float words for float kinds
+      ok = h0.x == kAnsMagicVersion && (int)(h1.x & 0xfu) == PB && nb == divUp(need, kBlockBytes);
+      if (KIND != kKindBytes) ok = ok && need == av.floatWords;
+      storedChecksum = KIND == kKindBytes ? h1.y : __ldg(reinterpret_cast<const uint32_t*>(md.in) + 3);
     }
-    if (memberOk) {
-      const uint8_t* pStates = av.ans + kAnsHeaderBytes + kAnsPdfBytes;
-      const uint2* pBlockWords = reinterpret_cast<const uint2*>(pStates + 128u * (size_t)nb);
-      const uint16_t* pData = reinterpret_cast<const uint16_t*>(
-          reinterpret_cast<const uint8_t*>(pBlockWords) + 8u * (size_t)roundUp(nb, 2u));
-      const bool canStage = (reinterpret_cast<uintptr_t>(av.ans) & 15u) == 0;
-      RowWriter<KIND> wr;
-      wr.setRing(smemAddr(sRing + warp * ringBytes), lane);
-      const uint32_t first = chunk * chunkBlocks;
-      const uint32_t last = min(nb, first + chunkBlocks);
-      for (uint32_t block = first + warp; block < last; block += WARPS) {
+    // ans/GpuANSDecode.cuh:326-337: success iff capacity suffices; size reported regardless
+    const bool memberOk = ok && md.size >= need;
+    if (t == 0 && atomicExch(sc.seen + m, 1u) == 0u) {
+      if (outSuccess) outSuccess[m] = memberOk ? 1 : 0;
+      if (outSize) outSize[m] = ok ? need : 0u;
+      if (wantChecksum) {
+        sc.archiveChecksum[m] = storedChecksum;
+        sc.sizes[m] = memberOk ? need : 0u;
+      }
+    }
+    const bool work = memberOk && nb > 0;
+    if (work) buildLut<PB, false, WARPS>(av.ans, lut, sPdf, sCdf, sWarp);
+
+    const uint8_t* pStates = av.ans + kAnsHeaderBytes + kAnsPdfBytes;
+    const uint2* pBlockWords = reinterpret_cast<const uint2*>(pStates + 128u * (size_t)nb);
+    const uint16_t* pData = reinterpret_cast<const uint16_t*>(
+        reinterpret_cast<const uint8_t*>(pBlockWords) + 8u * (size_t)roundUp(nb, 2u));
+    const bool canStage = (reinterpret_cast<uintptr_t>(av.ans) & 15u) == 0;
+    RowWriter<KIND> wr;
+    wr.setRing(smemAddr(sRing + warp * ringBytes), lane);
+
+    // ---- every warp claims blocks of the member until none are left ----
+    uint32_t block = sMisc[1];  // warp 0 starts with the block claimed with the lease
+    if (warp != 0) {
+      if (lane == 0) block = atomicAdd(sc.next + m, 1u);
+      block = __shfl_sync(0xffffffffu, block, 0);
+    }
+    while (block < blocksCap) {
+      uint32_t nextBlock = 0;
+      if (lane == 0) nextBlock = atomicAdd(sc.next + m, 1u);  // in flight while this block is decoded
+      if (work && block < nb) {
         const uint2 bw = __ldg(pBlockWords + block);
         const uint32_t blockLen = bw.x >> 16, words = bw.x & 0xffffu;
         const uint16_t* stream = pData + bw.y;
@@ -746,8 +742,9 @@ decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t chunkBlocks, uint32_t s
           decodeBlockWarp<KIND, PB, false>(state, st, blockLen, lut, wr, lane);
         }
       }
+      block = __shfl_sync(0xffffffffu, nextBlock, 0);
     }
-    __syncthreads();  // sMisc and the LUT are reused by the next step
+    __syncthreads();  // every warp is done with this member's LUT (and sMisc) before the next lease
   }
 }
 
@@ -776,7 +773,7 @@ DecodePlan planDecodeScratch(uint32_t n) {
   DecodePlan p{};
   size_t o = 0;
   p.members = o; o = alignUp256(o + sizeof(MemberDesc) * (size_t)n);
-  p.next = o; o = alignUp256(o + 4 * (size_t)n);
+  p.next = o; o = alignUp256(o + 8 * (size_t)n);  // next[n] then seen[n]
   p.totals = o; o = alignUp256(o + 4 * kMaxParts);
   p.checksum = o; o = alignUp256(o + 4 * (size_t)n);
   p.archiveChecksum = o; o = alignUp256(o + 4 * (size_t)n);
@@ -852,7 +849,7 @@ int launchDecodeW(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t pa
 }
 
 template <int KIND, int PB>
-int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks, uint32_t chunkBlocks,
+int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
                       uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
                       cudaStream_t stream) {
   constexpr int WARPS = 8;
@@ -880,20 +877,20 @@ int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
   const uint64_t resident = (uint64_t)perSm * smCountD();
   const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(resident, totalChunks));
   timerBegin(kSlotDecode, stream);
-  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, n, chunkBlocks, slotWords, outSuccess, outSize, checksum);
+  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, n, slotWords, outSuccess, outSize, checksum);
   DGB_CUDA_TRY(cudaGetLastError());
   timerEnd(kSlotDecode, stream);
   return DGB_OK;
 }
 
 template <int KIND>
-int decodeFusedKind(const DecodeScratch& sc, int pb, uint32_t n, uint64_t totalChunks, uint32_t chunkBlocks,
+int decodeFusedKind(const DecodeScratch& sc, int pb, uint32_t n, uint64_t totalChunks,
                     uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
                     cudaStream_t stream) {
   switch (pb) {
-    case 9: return launchDecodeFused<KIND, 9>(sc, n, totalChunks, chunkBlocks, slotWordsOpt, outSuccess, outSize, checksum, stream);
-    case 10: return launchDecodeFused<KIND, 10>(sc, n, totalChunks, chunkBlocks, slotWordsOpt, outSuccess, outSize, checksum, stream);
-    case 11: return launchDecodeFused<KIND, 11>(sc, n, totalChunks, chunkBlocks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+    case 9: return launchDecodeFused<KIND, 9>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+    case 10: return launchDecodeFused<KIND, 10>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+    case 11: return launchDecodeFused<KIND, 11>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
     default: return DGB_ERR_INVALID_ARG;
   }
 }
@@ -928,7 +925,6 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
 
   const Options opt = options();  // one snapshot per call
   const bool fused = opt.decode_fused != 0;
-  const uint32_t chunkBlocks = (uint32_t)std::max(1, std::min(opt.decode_chunk_blocks, 4096));
   static thread_local std::vector<MemberDesc> descStage;  // reused: no allocation on the steady-state path
   static thread_local std::vector<uint64_t> weightStage;
   descStage.resize(n);
@@ -943,15 +939,16 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     desc[i].in = members[i].in;
     desc[i].out = members[i].out;
     desc[i].size = members[i].size;  // capacity
-    // single-launch path: chunk count from the capacity (>= 1: every header is visited once)
-    const uint32_t chunks = std::max(1u, divUp(divUp(members[i].size, kBlockBytes), chunkBlocks));
-    desc[i].work0 = fused ? chunks : 0u;
-    totalChunks += chunks;
+    // single-launch path: block count bound from the capacity (>= 1: every header is visited once)
+    const uint32_t blocks = std::max(1u, divUp(members[i].size, kBlockBytes));
+    desc[i].work0 = fused ? blocks : 0u;
+    totalChunks += divUp(blocks, 8u);
   }
   uint8_t* base = static_cast<uint8_t*>(temp);
   DecodeScratch sc;
   sc.members = reinterpret_cast<MemberDesc*>(base + dp.members);
   sc.next = reinterpret_cast<uint32_t*>(base + dp.next);
+  sc.seen = sc.next + n;
   sc.totals = reinterpret_cast<uint32_t*>(base + dp.totals);
   sc.checksum = reinterpret_cast<uint32_t*>(base + dp.checksum);
   sc.archiveChecksum = reinterpret_cast<uint32_t*>(base + dp.archiveChecksum);
@@ -960,14 +957,14 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   if (checksum) DGB_CUDA_TRY(cudaMemsetAsync(sc.checksum, 0, 4 * (size_t)n, stream));
 
   if (fused) {
-    DGB_CUDA_TRY(cudaMemsetAsync(sc.next, 0, 4 * (size_t)n, stream));
+    DGB_CUDA_TRY(cudaMemsetAsync(sc.next, 0, 8 * (size_t)n, stream));
     const uint32_t slotOpt = opt.decode_slot_words > 0 ? (uint32_t)opt.decode_slot_words : 0u;
     int rc;
     switch (kind) {
-      case kKindBytes: rc = decodeFusedKind<kKindBytes>(sc, pb, n, totalChunks, chunkBlocks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
-      case kKindF16: rc = decodeFusedKind<kKindF16>(sc, pb, n, totalChunks, chunkBlocks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
-      case kKindBF16: rc = decodeFusedKind<kKindBF16>(sc, pb, n, totalChunks, chunkBlocks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
-      case kKindF32: rc = decodeFusedKind<kKindF32>(sc, pb, n, totalChunks, chunkBlocks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
+      case kKindBytes: rc = decodeFusedKind<kKindBytes>(sc, pb, n, totalChunks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
+      case kKindF16: rc = decodeFusedKind<kKindF16>(sc, pb, n, totalChunks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
+      case kKindBF16: rc = decodeFusedKind<kKindBF16>(sc, pb, n, totalChunks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
+      case kKindF32: rc = decodeFusedKind<kKindF32>(sc, pb, n, totalChunks, slotOpt, outSuccess_dev, outSize_dev, checksum, stream); break;
       default: return DGB_ERR_INVALID_ARG;
     }
     if (rc != DGB_OK) return rc;

@@ -37,7 +37,10 @@ namespace {
 
 constexpr int kStatsThreads = 256;  // == kNumSymbols: thread <-> symbol in the epilogue
 constexpr int kStatsWarps = kStatsThreads / 32;
-constexpr int kStatsUnroll = 4;     // independent 16 B loads in flight per thread
+#ifndef DGB_STATS_UNROLL
+#define DGB_STATS_UNROLL 4
+#endif
+constexpr int kStatsUnroll = DGB_STATS_UNROLL;     // independent 16 B loads in flight per thread
 
 __device__ __forceinline__ uint4 ldStream16(const uint4* p) {
   uint4 v;
@@ -46,6 +49,16 @@ __device__ __forceinline__ uint4 ldStream16(const uint4* p) {
                : "l"(p));
   return v;
 }
+
+// TMA landing buffer of a statistics item (fused launch): the item's whole slab arrives in shared
+// memory by one bulk copy (cp.async.bulk + mbarrier), so its HBM latency is covered by bytes in
+// flight, not by resident warps -- the item runs at full speed next to encoder CTAs.  The two-kernel
+// path (STAGED = false) keeps the register-pipelined global loads.
+struct StatsStage {
+  uint4* buf = nullptr;     // shared memory, 16 B aligned, >= slabVecs vectors
+  uint32_t bar = 0;         // shared address of the mbarrier
+  uint32_t* phase = nullptr;
+};
 
 struct EncodeScratch {
   MemberDesc* members;            // [n]
@@ -58,8 +71,6 @@ struct EncodeScratch {
   uint8_t* spill;                 // [resident warps][maxBlockWords] u16: overflow of small staging slots
   uint4* table;                   // [n][256] slots of 16 B (packed entries use the first half)
   bool wideTable;                 // entry format: EncEntryWide (16 B) or EncEntry (8 B)
-  uint8_t* compRows;              // float kinds: [n] rows of compStride bytes
-  uint32_t compStride;
   // fused single-launch encoder only
   const uint2* workIdx;           // [n + 1] {first stats item, first encode chunk} of member i
   uint32_t* ready;                // [n]  (zeroed) 1 once the member's table is published
@@ -234,11 +245,14 @@ __host__ __device__ inline uint32_t bytesSlabs(const void* in, uint32_t size, ui
 
 // Work of CTA y of Y on member m (Y = gridDim.y of the two-kernel path, the member's item count in
 // the fused kernel).  Returns true in the CTA that finished the member (its table is published).
+template <bool STAGED>
 __device__ __forceinline__ bool statsBytesItem(const EncodeScratch& sc, uint32_t (*sHist)[kNumSymbols],
                                                const uint32_t* __restrict__ histogramGiven, int pb,
                                                bool useChecksum, uint32_t slabVecs, uint32_t m, uint32_t y,
-                                               uint32_t Y, uint32_t* __restrict__ outSize) {
-  const uint32_t t = threadIdx.x, warp = t >> 5;
+                                               uint32_t Y, uint32_t* __restrict__ outSize,
+                                               const StatsStage& stage = StatsStage()) {
+  // shuffle => the histogram base is provably warp-uniform (ATOMS [R + UR], no per-symbol add)
+  const uint32_t t = threadIdx.x, warp = __shfl_sync(0xffffffffu, t >> 5, 0);
   const MemberDesc md = sc.members[m];
   const uint8_t* in = static_cast<const uint8_t*>(md.in);
   const uint32_t size = md.size;
@@ -257,6 +271,15 @@ __device__ __forceinline__ bool statsBytesItem(const EncodeScratch& sc, uint32_t
     if (y != 0) return false;
   } else {
     if (y >= participants) return false;
+    const uint4* vec = reinterpret_cast<const uint4*>(in + head);
+    if (STAGED && t == 0) {
+      const uint32_t v0 = y * slabVecs, v1 = min(nVec, v0 + slabVecs);
+      if (v1 > v0) {
+        fenceProxyAsync();  // the region was last touched through the generic proxy (coder staging)
+        mbarExpectTx(stage.bar, (v1 - v0) * 16u);
+        bulkLoad(smemAddr(stage.buf), vec + v0, (v1 - v0) * 16u, stage.bar);
+      }
+    }
 #pragma unroll
     for (int w = 0; w < kStatsWarps; ++w) sHist[w][t] = 0;
     __syncthreads();
@@ -266,15 +289,18 @@ __device__ __forceinline__ bool statsBytesItem(const EncodeScratch& sc, uint32_t
       if (t < head) { uint32_t b = in[t]; atomicAdd(&wh[b], 1u); xorAcc ^= b; }
       if (t < tail) { uint32_t b = in[head + nVec * 16u + t]; atomicAdd(&wh[b], 1u); xorAcc ^= b; }
     }
-    const uint4* vec = reinterpret_cast<const uint4*>(in + head);
     for (uint32_t slab = y; slab < nSlabs; slab += Y) {
       const uint32_t v0 = slab * slabVecs, v1 = min(nVec, v0 + slabVecs);
+      if (STAGED && v1 > v0) {  // one slab per item (Y == nSlabs): the copy was issued above
+        mbarWait(stage.bar, *stage.phase);
+        *stage.phase ^= 1u;
+      }
       for (uint32_t i0 = v0 + t; i0 < v1; i0 += kStatsUnroll * kStatsThreads) {
         uint4 vv[kStatsUnroll];
 #pragma unroll
         for (int k = 0; k < kStatsUnroll; ++k) {
           const uint32_t i = i0 + k * kStatsThreads;
-          vv[k] = i < v1 ? ldStream16(vec + i) : make_uint4(0, 0, 0, 0);
+          vv[k] = i < v1 ? (STAGED ? stage.buf[i - v0] : ldStream16(vec + i)) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int k = 0; k < kStatsUnroll; ++k) {
@@ -313,8 +339,8 @@ __global__ void __launch_bounds__(kStatsThreads)
 statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, int pb,
                  bool useChecksum, uint32_t slabVecs, uint32_t memberBase, uint32_t* __restrict__ outSize) {
   __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
-  statsBytesItem(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y,
-                 gridDim.y, outSize);
+  statsBytesItem<false>(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y,
+                        gridDim.y, outSize);
 }
 
 // ---------------------------------------------------------------------------
@@ -329,41 +355,13 @@ statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, 
 template <int FT>
 __device__ __forceinline__ uint32_t rot16x2(uint32_t w) {
   if (FT == DGB_BFLOAT16) {
-    // rotate both 16-bit halves left by one
-    return ((w << 1) & 0xfffefffeu) | ((w >> 15) & 0x00010001u);
+    // rotate both 16-bit halves left by one: bitwise select between w << 1 and w >> 15 under one
+    // mask, a single LOP3 (written as two AND/ORs, ptxas emits two LOP3s for the two constants)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(w << 1), "r"(w >> 15), "r"(0xfffefffeu));
+    return r;
   }
   return w;
-}
-
-// Stores of 8 / 4 consecutive bytes at an address that is only guaranteed the alignment of the
-// member's first vector (members whose input is not 16 B aligned shift every plane by `head`
-// elements).  The alignment is the same for every vector of a member, so the branch is uniform.
-__device__ __forceinline__ void storeBytes8(uint8_t* dst, uint2 v) {
-  const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 7u);
-  if (a == 0) {
-    *reinterpret_cast<uint2*>(dst) = v;
-  } else if ((a & 3u) == 0) {
-    reinterpret_cast<uint32_t*>(dst)[0] = v.x;
-    reinterpret_cast<uint32_t*>(dst)[1] = v.y;
-  } else if ((a & 1u) == 0) {
-    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-    d[0] = (uint16_t)v.x; d[1] = (uint16_t)(v.x >> 16); d[2] = (uint16_t)v.y; d[3] = (uint16_t)(v.y >> 16);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { dst[k] = (uint8_t)(v.x >> (8 * k)); dst[4 + k] = (uint8_t)(v.y >> (8 * k)); }
-  }
-}
-__device__ __forceinline__ void storeBytes4(uint8_t* dst, uint32_t v) {
-  const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
-  if (a == 0) {
-    *reinterpret_cast<uint32_t*>(dst) = v;
-  } else if ((a & 1u) == 0) {
-    reinterpret_cast<uint16_t*>(dst)[0] = (uint16_t)v;
-    reinterpret_cast<uint16_t*>(dst)[1] = (uint16_t)(v >> 16);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = (uint8_t)(v >> (8 * k));
-  }
 }
 
 // member = [head elements up to the first 16 B boundary | 16 B vectors | tail elements]
@@ -379,34 +377,63 @@ __host__ __device__ inline uint32_t floatSlabs(const void* in, uint32_t size, ui
   return s > 0u ? s : 1u;
 }
 
+// Histogram index (x4, the byte offset into a 256-bin u32 histogram) of the coded byte of the
+// element in bits [LO, LO + 16) of a packed 16-bit pair, or of a 32-bit word: one shift, one mask.
+//   fp16 coded = w >> 8, bf16 coded = (w >> 7) & 0xff, fp32 coded = (w >> 23) & 0xff
 template <int FT>
-__device__ __forceinline__ uint32_t splitScalar(const uint8_t* in, uint32_t e, uint8_t* comp, uint8_t* non,
-                                                uint32_t size) {
-  uint32_t c;
-  if (FT == DGB_FLOAT32) {
-    uint32_t w = reinterpret_cast<const uint32_t*>(in)[e];
-    w = __funnelshift_l(w, w, 1);
-    c = w >> 24;
-    reinterpret_cast<uint16_t*>(non)[e] = (uint16_t)(w & 0xffffu);
-    (non + 2u * roundUp(size, 8u))[e] = (uint8_t)((w >> 16) & 0xffu);
-  } else {
-    uint32_t w = reinterpret_cast<const uint16_t*>(in)[e];
-    if (FT == DGB_BFLOAT16) w = ((w << 1) | (w >> 15)) & 0xffffu;
-    c = w >> 8;
-    non[e] = (uint8_t)(w & 0xffu);
+__device__ __forceinline__ uint32_t histOffLo(uint32_t w) {  // low half (or the whole fp32 word)
+  return FT == DGB_FLOAT32 ? (w >> 21) & 0x3fcu : (w >> (FT == DGB_BFLOAT16 ? 5 : 6)) & 0x3fcu;
+}
+template <int FT>
+__device__ __forceinline__ uint32_t histOffHi(uint32_t w) {  // high half of a 16-bit pair
+  return (w >> (FT == DGB_BFLOAT16 ? 21 : 22)) & 0x3fcu;
+}
+__device__ __forceinline__ void histAdd(uint32_t* wh, uint32_t byteOff) {
+  atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(wh) + byteOff), 1u);
+}
+template <int FT>
+__device__ __forceinline__ uint32_t codedScalar(const uint8_t* in, uint32_t e) {
+  if (FT == DGB_FLOAT32) return (reinterpret_cast<const uint32_t*>(in)[e] >> 23) & 0xffu;
+  const uint32_t w = reinterpret_cast<const uint16_t*>(in)[e];
+  return FT == DGB_BFLOAT16 ? (w >> 7) & 0xffu : w >> 8;
+}
+
+// The vector body of a float statistics slab: vectors [v0, v1) of the member, 16 B each: a pure
+// read (the coder takes the coded byte out of the raw words itself and writes the stored planes).
+template <int FT, bool STAGED>
+__device__ __forceinline__ void histVectors(const uint4* __restrict__ vec, const StatsStage& stage, uint32_t v0,
+                                            uint32_t v1, uint32_t t, uint32_t* wh) {
+  for (uint32_t i0 = v0 + t; i0 < v1; i0 += kStatsUnroll * kStatsThreads) {
+    uint4 vv[kStatsUnroll];
+#pragma unroll
+    for (int k = 0; k < kStatsUnroll; ++k) {
+      const uint32_t i = i0 + k * kStatsThreads;
+      vv[k] = i < v1 ? (STAGED ? stage.buf[i - v0] : ldStream16(vec + i)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < kStatsUnroll; ++k) {
+      const uint32_t i = i0 + k * kStatsThreads;
+      if (i >= v1) break;
+      const uint32_t w4[4] = {vv[k].x, vv[k].y, vv[k].z, vv[k].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        histAdd(wh, histOffLo<FT>(w4[q]));
+        if (FT != DGB_FLOAT32) histAdd(wh, histOffHi<FT>(w4[q]));
+      }
+    }
   }
-  comp[e] = (uint8_t)c;
-  return c;
 }
 
 // Work of CTA y of Y on member m; returns true in the CTA that finished the member.
-template <int FT>
+template <int FT, bool STAGED>
 __device__ __forceinline__ bool statsFloatItem(const EncodeScratch& sc, uint32_t (*sHist)[kNumSymbols], int pb,
                                                bool useChecksum, uint32_t slabVecs, uint32_t m, uint32_t y,
-                                               uint32_t Y, uint32_t* __restrict__ outSize) {
+                                               uint32_t Y, uint32_t* __restrict__ outSize,
+                                               const StatsStage& stage = StatsStage()) {
   constexpr uint32_t EPV = (FT == DGB_FLOAT32) ? 4u : 8u;  // elements per 16 B vector
   constexpr uint32_t WB = (FT == DGB_FLOAT32) ? 4u : 2u;   // word bytes
-  const uint32_t t = threadIdx.x, warp = t >> 5;
+  // shuffle => the histogram base is provably warp-uniform (ATOMS [R + UR], no per-symbol add)
+  const uint32_t t = threadIdx.x, warp = __shfl_sync(0xffffffffu, t >> 5, 0);
   const MemberDesc md = sc.members[m];
   const uint8_t* in = static_cast<const uint8_t*>(md.in);
   const uint32_t size = md.size;  // float words
@@ -414,7 +441,6 @@ __device__ __forceinline__ bool statsFloatItem(const EncodeScratch& sc, uint32_t
   uint8_t* non = archive + kFloatHeaderBytes;
   const uint32_t nonBytes = floatNonCompBytes(FT, size);
   uint8_t* ansArchive = non + nonBytes;
-  uint8_t* comp = sc.compRows + (size_t)m * sc.compStride;
 
   const uint32_t head = floatHeadLen(in, size, WB);
   const uint32_t nVec = (size - head) / EPV;
@@ -425,6 +451,15 @@ __device__ __forceinline__ bool statsFloatItem(const EncodeScratch& sc, uint32_t
     if (y != 0) return false;
   } else {
     if (y >= participants) return false;
+    const uint4* vec = reinterpret_cast<const uint4*>(in + (size_t)head * WB);
+    if (STAGED && t == 0) {
+      const uint32_t v0 = y * slabVecs, v1 = min(nVec, v0 + slabVecs);
+      if (v1 > v0) {
+        fenceProxyAsync();  // the region was last touched through the generic proxy (coder staging)
+        mbarExpectTx(stage.bar, (v1 - v0) * 16u);
+        bulkLoad(smemAddr(stage.buf), vec + v0, (v1 - v0) * 16u, stage.bar);
+      }
+    }
 #pragma unroll
     for (int w = 0; w < kStatsWarps; ++w) sHist[w][t] = 0;
     __syncthreads();
@@ -432,72 +467,21 @@ __device__ __forceinline__ bool statsFloatItem(const EncodeScratch& sc, uint32_t
     uint32_t xorAcc = 0;
 
     // ---- vector body ----
-    const uint4* vec = reinterpret_cast<const uint4*>(in + (size_t)head * WB);
-    uint8_t* compV = comp + head;                 // plane positions of the first vector
-    uint8_t* nonV = non + (size_t)head * (FT == DGB_FLOAT32 ? 2u : 1u);
-    uint8_t* non1V = non + 2u * roundUp(size, 8u) + head;  // fp32: the u8 plane
     for (uint32_t slab = y; slab < nSlabs; slab += Y) {
       const uint32_t v0 = slab * slabVecs, v1 = min(nVec, v0 + slabVecs);
-      // four independent 16 B loads per thread are issued before any of them is consumed: the
-      // kernel is a pure stream and was latency-bound with one load in flight (ncu: 75 % of stall
-      // samples on the first use of the loaded vector, DRAM at 60 %)
-      for (uint32_t i0 = v0 + t; i0 < v1; i0 += kStatsUnroll * kStatsThreads) {
-        uint4 vv[kStatsUnroll];
-#pragma unroll
-        for (int k = 0; k < kStatsUnroll; ++k) {
-          const uint32_t i = i0 + k * kStatsThreads;
-          vv[k] = i < v1 ? ldStream16(vec + i) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int k = 0; k < kStatsUnroll; ++k) {
-          const uint32_t i = i0 + k * kStatsThreads;
-          if (i >= v1) break;
-          const uint4 v = vv[k];
-          if (FT == DGB_FLOAT32) {
-            const uint32_t r0 = __funnelshift_l(v.x, v.x, 1), r1 = __funnelshift_l(v.y, v.y, 1);
-            const uint32_t r2 = __funnelshift_l(v.z, v.z, 1), r3 = __funnelshift_l(v.w, v.w, 1);
-            // comp = top byte of each rotated word
-            const uint32_t c = __byte_perm(__byte_perm(r0, r1, 0x0073), __byte_perm(r2, r3, 0x0073), 0x5410);
-            storeBytes4(compV + 4u * (size_t)i, c);
-            // u16 plane: low halves
-            uint2 lo;
-            lo.x = __byte_perm(r0, r1, 0x5410);
-            lo.y = __byte_perm(r2, r3, 0x5410);
-            storeBytes8(nonV + 8u * (size_t)i, lo);
-            // u8 plane: byte 2 of each
-            const uint32_t hi = __byte_perm(__byte_perm(r0, r1, 0x0062), __byte_perm(r2, r3, 0x0062), 0x5410);
-            storeBytes4(non1V + 4u * (size_t)i, hi);
-            atomicAdd(&wh[c & 0xffu], 1u);
-            atomicAdd(&wh[(c >> 8) & 0xffu], 1u);
-            atomicAdd(&wh[(c >> 16) & 0xffu], 1u);
-            atomicAdd(&wh[c >> 24], 1u);
-          } else {
-            const uint32_t r0 = rot16x2<FT>(v.x), r1 = rot16x2<FT>(v.y);
-            const uint32_t r2 = rot16x2<FT>(v.z), r3 = rot16x2<FT>(v.w);
-            uint2 c, nn;
-            c.x = __byte_perm(r0, r1, 0x7531);
-            c.y = __byte_perm(r2, r3, 0x7531);
-            nn.x = __byte_perm(r0, r1, 0x6420);
-            nn.y = __byte_perm(r2, r3, 0x6420);
-            storeBytes8(compV + 8u * (size_t)i, c);
-            storeBytes8(nonV + 8u * (size_t)i, nn);
-            atomicAdd(&wh[c.x & 0xffu], 1u);
-            atomicAdd(&wh[(c.x >> 8) & 0xffu], 1u);
-            atomicAdd(&wh[(c.x >> 16) & 0xffu], 1u);
-            atomicAdd(&wh[c.x >> 24], 1u);
-            atomicAdd(&wh[c.y & 0xffu], 1u);
-            atomicAdd(&wh[(c.y >> 8) & 0xffu], 1u);
-            atomicAdd(&wh[(c.y >> 16) & 0xffu], 1u);
-            atomicAdd(&wh[c.y >> 24], 1u);
-          }
-        }
+      if (STAGED && v1 > v0) {  // one slab per item (Y == nSlabs): the copy was issued above
+        mbarWait(stage.bar, *stage.phase);
+        *stage.phase ^= 1u;
       }
+      // four independent 16 B loads per thread are issued before any of them is consumed: the
+      // kernel is a pure stream and was latency-bound with one load in flight
+      histVectors<FT, STAGED>(vec, stage, v0, v1, t, wh);
     }
     if (y == 0) {
       // ---- scalar head and tail (fewer than one vector each) ----
       const uint32_t tailStart = head + nVec * EPV;
-      if (t < head) atomicAdd(&wh[splitScalar<FT>(in, t, comp, non, size)], 1u);
-      if (t < size - tailStart) atomicAdd(&wh[splitScalar<FT>(in, tailStart + t, comp, non, size)], 1u);
+      if (t < head) atomicAdd(&wh[codedScalar<FT>(in, t)], 1u);
+      if (t < size - tailStart) atomicAdd(&wh[codedScalar<FT>(in, tailStart + t)], 1u);
       // float header (float/GpuFloatCompress.cuh:324-337) and zero padding of the planes
       if (t == 0) {
         // float-level checksum is patched in by the epilogue CTA
@@ -544,7 +528,7 @@ __global__ void __launch_bounds__(kStatsThreads)
 statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, uint32_t memberBase,
                  uint32_t* __restrict__ outSize) {
   __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
-  statsFloatItem<FT>(sc, sHist, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y, gridDim.y, outSize);
+  statsFloatItem<FT, false>(sc, sHist, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y, gridDim.y, outSize);
 }
 
 // ---------------------------------------------------------------------------
@@ -561,8 +545,7 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
 #ifndef DGB_ENC_GROUP_ROWS
 #define DGB_ENC_GROUP_ROWS 16
 #endif
-constexpr int kEncGroupRows = DGB_ENC_GROUP_ROWS;  // rows per cp.async group (16: all lanes copy 16 B; 8: lanes 0..15)
-constexpr uint32_t kEncRingSlots = 4;  // groups resident per warp
+constexpr int kEncGroupRows = DGB_ENC_GROUP_ROWS;  // rows per cp.async group
 
 __device__ __forceinline__ void cpAsync16(uint32_t dstSmem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstSmem), "l"(src) : "memory");
@@ -577,6 +560,135 @@ __device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
   return v;
+}
+
+// ---------------------------------------------------------------------------
+// Input side of the coder, per data kind.  The coder reads the member's RAW words (bytes, or the
+// fp16 / bf16 / fp32 words themselves): for float kinds it takes the coded byte out of each word on
+// the way to the table lookup and writes the stored plane(s) of the float archive from the same
+// shared-memory copy of the input.  The reference (and round 1 here) splits in a separate pass that
+// writes the coded bytes to scratch for the coder to read back (float/GpuFloatCompress.cuh:280-365):
+// one byte per element written and one read, which is a quarter of the statistics pass's traffic;
+// here the statistics pass is a pure read.
+//   fp16 : coded = w >> 8,        stored = w & 0xff                     (float/GpuFloatUtils.cuh:111-119)
+//   bf16 : coded = (w >> 7) & ff, stored = (w & 7f) << 1 | w >> 15      (:141-159)
+//   fp32 : coded = (w >> 23) & ff, stored = low 24 bits of rotl(w, 1): u16 plane then u8 plane (:181-203)
+// ---------------------------------------------------------------------------
+struct StoredPlanes {
+  uint8_t* non;   // fp16 / bf16: the stored byte plane; fp32: the u16 plane
+  uint8_t* non1;  // fp32: the u8 plane
+};
+
+template <int KIND>
+struct EncIn;
+
+template <>
+struct EncIn<kKindBytes> {
+  static constexpr uint32_t kWordBytes = 1, kRingSlots = 4;
+  template <int J, uint32_t STRIDE>
+  static __device__ __forceinline__ uint32_t tabOffset(uint32_t ringLane) {
+    return STRIDE * ldsU8<J * 32>(ringLane);
+  }
+  template <uint32_t STRIDE>
+  static __device__ __forceinline__ uint32_t tabOffsetOf(uint32_t w) { return STRIDE * w; }
+  static __device__ __forceinline__ uint32_t loadWord(const uint8_t* in, uint32_t e) { return in[e]; }
+  static __device__ __forceinline__ void storeScalar(const StoredPlanes&, uint32_t, uint32_t) {}
+  static __device__ __forceinline__ void storeGroup(uint32_t, const StoredPlanes&, uint32_t, uint32_t) {}
+};
+
+#ifndef DGB_ENC_RING16
+#define DGB_ENC_RING16 3  // 3 slots = 3 KiB per warp: 4 CTAs per SM (4 slots: 3), c3 encode 195 -> 189 us
+#endif
+template <int KIND>
+struct EncIn16 {
+  static constexpr uint32_t kWordBytes = 2, kRingSlots = DGB_ENC_RING16;
+  static constexpr uint32_t kCodedBit = KIND == kKindBF16 ? 7u : 8u;
+  template <uint32_t STRIDE>
+  static __device__ __forceinline__ uint32_t tabOffsetOf(uint32_t w) {
+    // STRIDE * ((w >> kCodedBit) & 0xff) in one shift and one mask (STRIDE is 8 or 16)
+    constexpr uint32_t lg = STRIDE == 16 ? 4u : 3u;
+    return (w >> (kCodedBit - lg)) & (0xffu << lg);
+  }
+  template <int J, uint32_t STRIDE>
+  static __device__ __forceinline__ uint32_t tabOffset(uint32_t ringLane) {
+    uint32_t w;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(w) : "r"(ringLane), "n"(J * 64));
+    return tabOffsetOf<STRIDE>(w);
+  }
+  static __device__ __forceinline__ uint32_t loadWord(const uint8_t* in, uint32_t e) {
+    return __ldg(reinterpret_cast<const uint16_t*>(in) + e);
+  }
+  static __device__ __forceinline__ uint32_t storedOf(uint32_t w) {
+    return KIND == kKindBF16 ? (((w << 1) | (w >> 15)) & 0xffu) : (w & 0xffu);
+  }
+  static __device__ __forceinline__ void storeScalar(const StoredPlanes& pl, uint32_t e, uint32_t w) {
+    pl.non[e] = (uint8_t)storedOf(w);
+  }
+  // stored bytes of one group of 16 rows (512 elements, 1 KiB in the ring slot at `slot`): lane l
+  // handles the 16 B vectors l and l + 32 -> 8 stored bytes each, one 8 B store
+  static __device__ __forceinline__ void storeGroup(uint32_t slot, const StoredPlanes& pl, uint32_t elem0,
+                                                    uint32_t lane) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t v = lane + 32u * h;
+      uint4 x;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(slot + v * 16u));
+      const uint32_t r0 = rot16x2<KIND>(x.x), r1 = rot16x2<KIND>(x.y), r2 = rot16x2<KIND>(x.z), r3 = rot16x2<KIND>(x.w);
+      uint2 nn;
+      nn.x = __byte_perm(r0, r1, 0x6420);
+      nn.y = __byte_perm(r2, r3, 0x6420);
+      *reinterpret_cast<uint2*>(pl.non + elem0 + v * 8u) = nn;
+    }
+  }
+};
+template <> struct EncIn<kKindF16> : EncIn16<kKindF16> {};
+template <> struct EncIn<kKindBF16> : EncIn16<kKindBF16> {};
+
+template <>
+struct EncIn<kKindF32> {
+  static constexpr uint32_t kWordBytes = 4, kRingSlots = 3;
+  template <uint32_t STRIDE>
+  static __device__ __forceinline__ uint32_t tabOffsetOf(uint32_t w) {
+    constexpr uint32_t lg = STRIDE == 16 ? 4u : 3u;
+    return (w >> (23u - lg)) & (0xffu << lg);
+  }
+  template <int J, uint32_t STRIDE>
+  static __device__ __forceinline__ uint32_t tabOffset(uint32_t ringLane) {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w) : "r"(ringLane), "n"(J * 128));
+    return tabOffsetOf<STRIDE>(w);
+  }
+  static __device__ __forceinline__ uint32_t loadWord(const uint8_t* in, uint32_t e) {
+    return __ldg(reinterpret_cast<const uint32_t*>(in) + e);
+  }
+  static __device__ __forceinline__ void storeScalar(const StoredPlanes& pl, uint32_t e, uint32_t w) {
+    const uint32_t r = __funnelshift_l(w, w, 1);
+    reinterpret_cast<uint16_t*>(pl.non)[e] = (uint16_t)r;
+    pl.non1[e] = (uint8_t)(r >> 16);
+  }
+  // one group of 16 rows = 512 words = 2 KiB in the ring slot: lane l handles vectors l + 32 h
+  static __device__ __forceinline__ void storeGroup(uint32_t slot, const StoredPlanes& pl, uint32_t elem0,
+                                                    uint32_t lane) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const uint32_t v = lane + 32u * h;
+      uint4 x;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(slot + v * 16u));
+      const uint32_t r0 = __funnelshift_l(x.x, x.x, 1), r1 = __funnelshift_l(x.y, x.y, 1);
+      const uint32_t r2 = __funnelshift_l(x.z, x.z, 1), r3 = __funnelshift_l(x.w, x.w, 1);
+      uint2 lo;
+      lo.x = __byte_perm(r0, r1, 0x5410);
+      lo.y = __byte_perm(r2, r3, 0x5410);
+      *reinterpret_cast<uint2*>(pl.non + 2u * (size_t)(elem0 + v * 4u)) = lo;
+      const uint32_t hi = __byte_perm(__byte_perm(r0, r1, 0x0062), __byte_perm(r2, r3, 0x0062), 0x5410);
+      *reinterpret_cast<uint32_t*>(pl.non1 + elem0 + v * 4u) = hi;
+    }
+  }
+};
+
+__host__ __device__ constexpr uint32_t encRingBytes(int kind) {
+  return kind == kKindBytes ? 4u * kEncGroupRows * 32u
+                            : (kind == kKindF32 ? 3u * kEncGroupRows * 128u : (uint32_t)DGB_ENC_RING16 * kEncGroupRows * 64u);
 }
 
 // One rANS step for a full row (ans/GpuANSEncode.cuh:49-90 restated).  The
@@ -699,18 +811,18 @@ __device__ __forceinline__ void encodeUpdate(uint32_t& state, const EncSym<WIDE>
 }
 
 template <bool WIDE>
-__device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t sym, const EncRegs& rc, uint32_t& wa) {
+__device__ __forceinline__ void encodeStep(uint32_t& state, uint32_t tabOff, const EncRegs& rc, uint32_t& wa) {
   EncSym<WIDE> e;
-  e.load(rc.tabAddr + sym * EncSym<WIDE>::kStride, rc);
+  e.load(rc.tabAddr + tabOff, rc);
   emitWords<!WIDE>(state, e.thr, wa, rc.ltMask, rc.one);
   encodeUpdate(state, e);
 }
 
 template <bool WIDE>
-__device__ __forceinline__ void encodeStepPartial(bool valid, uint32_t& state, uint32_t sym,
+__device__ __forceinline__ void encodeStepPartial(bool valid, uint32_t& state, uint32_t tabOff,
                                                   const EncRegs& rc, uint32_t& wa) {
   EncSym<WIDE> e;
-  e.load(rc.tabAddr + sym * EncSym<WIDE>::kStride, rc);
+  e.load(rc.tabAddr + tabOff, rc);
   // invalid lanes never emit: compare against an unreachable threshold
   emitWords<!WIDE>(state, valid ? e.thr : 0xffffffffu, wa, rc.ltMask, rc.one);
   uint32_t next = state;
@@ -721,25 +833,25 @@ __device__ __forceinline__ void encodeStepPartial(bool valid, uint32_t& state, u
 // One group of kEncGroupRows rows.  The symbol bytes and the table entries do not depend on
 // the coder state, so they are fetched ahead of the serial state chain: all symbols of the
 // group first, then table entries kept kDepth rows ahead of the row being coded.
-template <int J, uint32_t STRIDE>
+template <int KIND, int J, uint32_t STRIDE>
 struct EncLoad {
   static __device__ __forceinline__ void syms(uint32_t ringLane, uint32_t tabAddr, uint32_t* addr) {
-    EncLoad<J - 1, STRIDE>::syms(ringLane, tabAddr, addr);
-    addr[J - 1] = tabAddr + STRIDE * ldsU8<(J - 1) * 32>(ringLane);
+    EncLoad<KIND, J - 1, STRIDE>::syms(ringLane, tabAddr, addr);
+    addr[J - 1] = tabAddr + EncIn<KIND>::template tabOffset<J - 1, STRIDE>(ringLane);
   }
 };
-template <uint32_t STRIDE>
-struct EncLoad<0, STRIDE> {
+template <int KIND, uint32_t STRIDE>
+struct EncLoad<KIND, 0, STRIDE> {
   static __device__ __forceinline__ void syms(uint32_t, uint32_t, uint32_t*) {}
 };
 
-template <bool WIDE>
+template <bool WIDE, int KIND>
 __device__ __forceinline__ void encodeGroup(uint32_t& state, uint32_t ringLane, const EncRegs& rc,
                                             uint32_t& wa) {
   constexpr int U = kEncGroupRows;
   constexpr int kDepth = 4;
   uint32_t addr[U];
-  EncLoad<U, EncSym<WIDE>::kStride>::syms(ringLane, rc.tabAddr, addr);
+  EncLoad<KIND, U, EncSym<WIDE>::kStride>::syms(ringLane, rc.tabAddr, addr);
   EncSym<WIDE> e[kDepth];
 #pragma unroll
   for (int j = 0; j < kDepth; ++j) e[j].load(addr[j], rc);
@@ -778,16 +890,22 @@ __device__ __forceinline__ void spillOut(Spill& sp, uint32_t stageAddr, uint16_t
   wa = stageAddr + 2u * left;
 }
 
-// Encodes bytes [0, n) of one block with one warp into the staging slot at
-// shared byte address `stageAddr` (spilling to sp.area when the slot is small).
-// Returns the TOTAL word count; the words not yet spilled are stage[0 .. total - sp.spilled).
-template <bool WIDE>
-__device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ in, uint32_t n,
-                                                    uint32_t tabAddr, int pb, uint32_t stageAddr,
-                                                    uint16_t* stage, Spill& sp,
-                                                    uint32_t ringAddr, uint32_t lane,
-                                                    uint32_t& stateOut) {
+// Encodes elements [0, n) of one block (raw words of data kind KIND at `in`; `elem0` = index of the
+// block's first element in its member) with one warp into the staging slot at shared byte address
+// `stageAddr` (spilling to sp.area when the slot is small); float kinds also write the block's
+// stored plane(s).  Returns the TOTAL word count; the words not yet spilled are
+// stage[0 .. total - sp.spilled).
+template <bool WIDE, int KIND>
+__device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ in, uint32_t n, uint32_t elem0,
+                                                    const StoredPlanes& planes, uint32_t tabAddr, int pb,
+                                                    uint32_t stageAddr, uint16_t* stage, Spill& sp,
+                                                    uint32_t ringAddr, uint32_t lane, uint32_t& stateOut) {
+  typedef EncIn<KIND> In;
   constexpr int U = kEncGroupRows;
+  constexpr uint32_t WB = In::kWordBytes;
+  constexpr uint32_t kGroupBytes = U * 32 * WB;     // 512 B, 1 KiB or 2 KiB
+  constexpr uint32_t kChunks = kGroupBytes / 512u;  // 16 B copies per lane and group
+  constexpr uint32_t kStride = EncSym<WIDE>::kStride;
   uint32_t state = kStateMin;
   uint32_t wa = stageAddr;
   const EncRegs rc = makeEncRegs(tabAddr, pb);
@@ -799,35 +917,46 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
     const uint32_t groups = fullRows / U;
     const uint8_t* src = in + lane * 16u;
     const uint32_t dst = ringAddr + lane * 16u;
-    const bool copier = lane < (uint32_t)(U * 2);  // U*32 bytes per group, 16 B per copying lane
-    if (groups > 0 && copier) cpAsync16(dst, src);
+    auto issue = [&](uint32_t g, uint32_t slot) {
+#pragma unroll
+      for (uint32_t c = 0; c < kChunks; ++c)
+        cpAsync16(dst + slot * kGroupBytes + c * 512u, src + (size_t)g * kGroupBytes + c * 512u);
+    };
+    if (groups > 0) issue(0, 0);
     cpAsyncCommit();
-    if (groups > 1 && copier) cpAsync16(dst + U * 32, src + U * 32);
+    if (groups > 1) issue(1, 1);
     cpAsyncCommit();
+    uint32_t slot = 0, slotNext = 2 % In::kRingSlots;
     for (uint32_t k = 0; k < groups; ++k) {
-      if (k + 2 < groups && copier)
-        cpAsync16(dst + ((k + 2) & (kEncRingSlots - 1)) * (U * 32), src + (k + 2) * (U * 32));
+      if (k + 2 < groups) issue(k + 2, slotNext);
       cpAsyncCommit();
       if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
       cpAsyncWait<2>();
       __syncwarp();
-      encodeGroup<WIDE>(state, ringAddr + (k & (kEncRingSlots - 1)) * (U * 32) + lane, rc, wa);
+      const uint32_t slotAddr = ringAddr + slot * kGroupBytes;
+      if (KIND != kKindBytes) In::storeGroup(slotAddr, planes, elem0 + k * (U * 32), lane);
+      encodeGroup<WIDE, KIND>(state, slotAddr + lane * WB, rc, wa);
+      slot = slot + 1 == In::kRingSlots ? 0u : slot + 1;
+      slotNext = slotNext + 1 == In::kRingSlots ? 0u : slotNext + 1;
     }
     r = groups * U;
   }
   // remaining rows (fewer than U, or all of them when the input is not 16 B aligned): every U rows
   // the same spill check as above
-  const uint8_t* p = in + lane + r * 32u;
-  for (uint32_t j = 0; r < fullRows; ++r, ++j, p += 32) {
+  uint32_t e = r * 32u + lane;
+  for (uint32_t j = 0; r < fullRows; ++r, ++j, e += 32) {
     if (sp.area && (j % U) == 0 && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
-    encodeStep<WIDE>(state, p[0], rc, wa);
+    const uint32_t w = In::loadWord(in, e);
+    In::storeScalar(planes, elem0 + e, w);
+    encodeStep<WIDE>(state, In::template tabOffsetOf<kStride>(w), rc, wa);
   }
   const uint32_t rem = n & 31u;
   if (rem) {
     if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
     const bool valid = lane < rem;
-    const uint32_t sym = valid ? p[0] : 0u;
-    encodeStepPartial<WIDE>(valid, state, sym, rc, wa);
+    const uint32_t w = valid ? In::loadWord(in, e) : 0u;
+    if (valid) In::storeScalar(planes, elem0 + e, w);
+    encodeStepPartial<WIDE>(valid, state, In::template tabOffsetOf<kStride>(w), rc, wa);
   }
   stateOut = state;
   return sp.spilled + ((wa - stageAddr) >> 1);
@@ -879,22 +1008,24 @@ __device__ __forceinline__ uint32_t lookbackWarp(volatile unsigned long long* de
 }
 
 // dynamic shared memory per warp: [table 2 KiB][input ring 2 KiB][staging slot]
-__host__ __device__ constexpr uint32_t encWarpSmem(int pb) {
-  return kNumSymbols * 8u + kEncRingSlots * kEncGroupRows * 32u + maxBlockWords(pb) * 2u;
+__host__ __device__ constexpr uint32_t encWarpSmem(int pb, int kind) {
+  return kNumSymbols * 8u + encRingBytes(kind) + maxBlockWords(pb) * 2u;
 }
 
-__global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksum,
+template <int KIND>
+__global__ void encodeKernel(EncodeScratch sc, int pb, bool useChecksum,
                              uint32_t numMembers, uint32_t totalTickets,
                              uint32_t* __restrict__ outSize) {
+  constexpr int kind = KIND;
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t t = threadIdx.x, lane = t & 31u;
   // shuffle => provably warp-uniform (no divergence check around the votes in the hot loop)
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  uint8_t* mine = smem + (size_t)warp * encWarpSmem(pb);
+  uint8_t* mine = smem + (size_t)warp * encWarpSmem(pb, kind);
   uint4* myTab = reinterpret_cast<uint4*>(mine);
   const uint32_t tabAddr = smemAddr(mine);
   const uint32_t ringAddr = tabAddr + kNumSymbols * 8u;
-  uint16_t* myStage = reinterpret_cast<uint16_t*>(mine + kNumSymbols * 8u + kEncRingSlots * kEncGroupRows * 32u);
+  uint16_t* myStage = reinterpret_cast<uint16_t*>(mine + kNumSymbols * 8u + encRingBytes(kind));
   const uint32_t stageAddr = smemAddr(myStage);
   volatile unsigned long long* desc = sc.lookback;
   uint32_t curMember = 0xffffffffu;
@@ -919,13 +1050,17 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
     const uint8_t* ansIn;
     uint8_t* ansOut;
     uint32_t extraBytes = 0;
+    StoredPlanes planes{nullptr, nullptr};
+    ansIn = static_cast<const uint8_t*>(md.in);
     if (kind == kKindBytes) {
-      ansIn = static_cast<const uint8_t*>(md.in);
       ansOut = static_cast<uint8_t*>(md.out);
     } else {
-      ansIn = sc.compRows + (size_t)m * sc.compStride;
       extraBytes = kFloatHeaderBytes + floatNonCompBytes(kind, size);
       ansOut = static_cast<uint8_t*>(md.out) + extraBytes;
+      planes.non = static_cast<uint8_t*>(md.out) + kFloatHeaderBytes;
+      planes.non1 = planes.non + 2u * roundUp(size, 8u);
+      __builtin_assume(__isGlobal(planes.non));
+      __builtin_assume(__isGlobal(planes.non1));
     }
     __builtin_assume(__isGlobal(ansIn));
     __builtin_assume(__isGlobal(ansOut));
@@ -944,7 +1079,8 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
     const uint32_t blockLen = min(kBlockBytes, size - start);
     uint32_t state;
     Spill sp{nullptr, 0u, 0u};  // worst-case sized slot: never spills
-    const uint32_t words = encodeBlockWarp<false>(ansIn + start, blockLen, tabAddr, pb, stageAddr, myStage, sp, ringAddr, lane, state);
+    const uint32_t words = encodeBlockWarp<false, KIND>(ansIn + (size_t)start * EncIn<KIND>::kWordBytes, blockLen, start, planes,
+                                                        tabAddr, pb, stageAddr, myStage, sp, ringAddr, lane, state);
     const uint32_t padded = roundUp(words, 8u);
 
     // ---- packed offset of this block: look-back over the member's earlier tickets ----
@@ -995,8 +1131,8 @@ __global__ void encodeKernel(EncodeScratch sc, int kind, int pb, bool useChecksu
 // member by member (one shared table load per member) and its warps stride
 // over the blocks of the member.
 // ---------------------------------------------------------------------------
-__host__ __device__ constexpr uint32_t encFastWarpSmem(uint32_t slotWords) {
-  return kEncRingSlots * kEncGroupRows * 32u + slotWords * 2u;  // ring + staging
+__host__ __device__ constexpr uint32_t encFastWarpSmem(uint32_t slotWords, int kind) {
+  return encRingBytes(kind) + slotWords * 2u;  // ring + staging
 }
 
 // Per-warp view of the CTA's dynamic shared memory: [input ring | staging slot] per warp.
@@ -1006,16 +1142,16 @@ struct WarpSmem {
   Spill sp;
 };
 __device__ __forceinline__ WarpSmem warpSmem(const EncodeScratch& sc, uint8_t* smem, uint32_t warp, uint32_t W,
-                                             uint32_t slotWords, int pb, uint32_t spillWarpBase) {
+                                             uint32_t slotWords, int pb, int kind, uint32_t spillWarpBase) {
   WarpSmem ws;
-  uint8_t* mine = smem + (size_t)warp * encFastWarpSmem(slotWords);
+  uint8_t* mine = smem + (size_t)warp * encFastWarpSmem(slotWords, kind);
   ws.ringAddr = smemAddr(mine);
   ws.sp.area = slotWords < maxBlockWords(pb)
                    ? reinterpret_cast<uint16_t*>(sc.spill) + (size_t)(spillWarpBase + blockIdx.x * W + warp) * maxBlockWords(pb)
                    : nullptr;
   ws.sp.limitBytes = (slotWords - kEncGroupRows * 32u - 8u) * 2u;  // a group emits at most 16*32 words
   ws.sp.spilled = 0;
-  ws.stage = reinterpret_cast<uint16_t*>(mine + kEncRingSlots * kEncGroupRows * 32u);
+  ws.stage = reinterpret_cast<uint16_t*>(mine + encRingBytes(kind));
   ws.stageAddr = smemAddr(ws.stage);
   return ws;
 }
@@ -1030,24 +1166,29 @@ __device__ __forceinline__ void loadTable(const EncodeScratch& sc, uint4* sTab, 
 // Warps of the CTA encode blocks [first, last) of member m (block k by warp (k - first) % W): the
 // 32-lane rANS state machine per block, then the block takes its place in the archive's data
 // section with one 64-bit atomic.
-template <bool WIDE>
+template <bool WIDE, int KIND>
 __device__ __forceinline__ void encodeMemberBlocks(const EncodeScratch& sc, const MemberDesc& md, uint32_t m,
-                                                   uint32_t first, uint32_t last, int kind, int pb,
+                                                   uint32_t first, uint32_t last, int pb,
                                                    bool useChecksum, uint32_t tabAddr, WarpSmem& ws,
                                                    uint32_t warp, uint32_t W, uint32_t lane,
                                                    uint32_t* __restrict__ outSize) {
+  constexpr int kind = KIND;
   const uint32_t size = md.size;
   const uint32_t nb = divUp(size, kBlockBytes);
   const uint8_t* ansIn;
   uint8_t* ansOut;
   uint32_t extraBytes = 0;
+  StoredPlanes planes{nullptr, nullptr};
+  ansIn = static_cast<const uint8_t*>(md.in);
   if (kind == kKindBytes) {
-    ansIn = static_cast<const uint8_t*>(md.in);
     ansOut = static_cast<uint8_t*>(md.out);
   } else {
-    ansIn = sc.compRows + (size_t)m * sc.compStride;
     extraBytes = kFloatHeaderBytes + floatNonCompBytes(kind, size);
     ansOut = static_cast<uint8_t*>(md.out) + extraBytes;
+    planes.non = static_cast<uint8_t*>(md.out) + kFloatHeaderBytes;
+    planes.non1 = planes.non + 2u * roundUp(size, 8u);
+    __builtin_assume(__isGlobal(planes.non));
+    __builtin_assume(__isGlobal(planes.non1));
   }
   __builtin_assume(__isGlobal(ansIn));
   __builtin_assume(__isGlobal(ansOut));
@@ -1059,8 +1200,8 @@ __device__ __forceinline__ void encodeMemberBlocks(const EncodeScratch& sc, cons
     const uint32_t start = block * kBlockBytes;
     const uint32_t blockLen = min(kBlockBytes, size - start);
     uint32_t state;
-    const uint32_t words = encodeBlockWarp<WIDE>(ansIn + start, blockLen, tabAddr, pb, ws.stageAddr, ws.stage, ws.sp,
-                                                 ws.ringAddr, lane, state);
+    const uint32_t words = encodeBlockWarp<WIDE, KIND>(ansIn + (size_t)start * EncIn<KIND>::kWordBytes, blockLen, start, planes,
+                                                       tabAddr, pb, ws.stageAddr, ws.stage, ws.sp, ws.ringAddr, lane, state);
     const uint32_t padded = roundUp(words, 8u);
     // take a place in the data section: one 64-bit atomic hands out the word offset (low half)
     // and counts finished blocks (high half), so no fence is needed to order the two
@@ -1087,9 +1228,9 @@ __device__ __forceinline__ void encodeMemberBlocks(const EncodeScratch& sc, cons
   }
 }
 
-template <bool WIDE>
+template <bool WIDE, int KIND>
 __global__ void
-encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
+encodeKernelFast(EncodeScratch sc, int pb, bool useChecksum,
                                  uint32_t numMembers, uint32_t blockBegin, uint32_t blockEnd,
                                  uint32_t slotWords, uint32_t spillWarpBase,
                                  uint32_t* __restrict__ outSize) {
@@ -1099,7 +1240,7 @@ encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
   const uint32_t t = threadIdx.x, lane = t & 31u;
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
   const uint32_t W = blockDim.x >> 5;
-  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, spillWarpBase);
+  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, KIND, spillWarpBase);
   const uint32_t tabAddr = smemAddr(sTab);
 
   const uint64_t g = gridDim.x, span = blockEnd - blockBegin;
@@ -1122,8 +1263,8 @@ encodeKernelFast(EncodeScratch sc, int kind, int pb, bool useChecksum,
     const uint32_t memberEnd = min(end, md.work0 + nb);
     loadTable<WIDE>(sc, sTab, m);
     __syncthreads();
-    encodeMemberBlocks<WIDE>(sc, md, m, cur - md.work0, memberEnd - md.work0, kind, pb, useChecksum, tabAddr, ws,
-                             warp, W, lane, outSize);
+    encodeMemberBlocks<WIDE, KIND>(sc, md, m, cur - md.work0, memberEnd - md.work0, pb, useChecksum, tabAddr, ws,
+                                   warp, W, lane, outSize);
     cur = memberEnd;
     __syncthreads();  // table is replaced for the next member
   }
@@ -1158,7 +1299,7 @@ __device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v) {
 enum FusedAct : uint32_t { kActExit = 0, kActWait = 1, kActStats = 2, kActEncode = 3 };
 constexpr uint32_t kNoChunk = 0xffffffffu;
 
-template <int KIND, bool WIDE>
+template <int KIND, bool WIDE, bool STAGED>
 __global__ void __launch_bounds__(kStatsThreads, 4)
 encodeFusedKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, int pb, bool useChecksum,
                   uint32_t numMembers, uint32_t totalItems, uint32_t totalChunks, uint32_t slabVecs,
@@ -1169,11 +1310,24 @@ encodeFusedKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven,
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(16) uint4 sTab[WIDE ? kNumSymbols : kNumSymbols / 2];
   __shared__ uint32_t sCtl[8];
+  __shared__ __align__(8) unsigned long long sStageBar;
   uint32_t (*sHist)[kNumSymbols] = reinterpret_cast<uint32_t (*)[kNumSymbols]>(smem);
   const uint32_t t = threadIdx.x, lane = t & 31u;
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
   constexpr uint32_t W = kStatsThreads / 32;
-  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, 0u);
+  // statistics items: histograms in the first 8 KiB of the dynamic region, the slab's landing
+  // buffer in the rest (the host sizes slabVecs to fit)
+  uint32_t stagePhase = 0;
+  StatsStage stage;
+  stage.buf = reinterpret_cast<uint4*>(smem + sizeof(uint32_t) * kStatsWarps * kNumSymbols);
+  stage.bar = smemAddr(&sStageBar);
+  stage.phase = &stagePhase;
+  if (STAGED) {
+    if (t == 0) mbarInit(stage.bar, 1);
+    fenceBarrierInit();
+    __syncthreads();
+  }
+  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, KIND, 0u);
   const uint32_t tabAddr = smemAddr(sTab);
   const bool preferStats = statsEvery != 0u && (blockIdx.x % statsEvery) == 0u;
 
@@ -1218,10 +1372,11 @@ encodeFusedKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven,
       const uint2 w0 = __ldg(&sc.workIdx[m]), w1 = __ldg(&sc.workIdx[m + 1]);
       bool finished;
       if (KIND == kKindBytes) {
-        finished = statsBytesItem(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, m, arg - w0.x, w1.x - w0.x, outSize);
+        finished = statsBytesItem<STAGED>(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, m, arg - w0.x,
+                                          w1.x - w0.x, outSize, stage);
       } else {
-        finished = statsFloatItem<KIND == kKindBytes ? DGB_FLOAT16 : KIND>(sc, sHist, pb, useChecksum, slabVecs, m,
-                                                                            arg - w0.x, w1.x - w0.x, outSize);
+        finished = statsFloatItem<KIND == kKindBytes ? DGB_FLOAT16 : KIND, STAGED>(
+            sc, sHist, pb, useChecksum, slabVecs, m, arg - w0.x, w1.x - w0.x, outSize, stage);
       }
       if (finished) {
         // table, pdf and (through the ticket chain) every comp / stored byte of the member are
@@ -1239,8 +1394,8 @@ encodeFusedKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven,
       }
       const uint32_t nb = divUp(md.size, kBlockBytes);
       const uint32_t first = (arg - __ldg(&sc.workIdx[m].y)) * chunkBlocks;
-      encodeMemberBlocks<WIDE>(sc, md, m, first, min(nb, first + chunkBlocks), KIND, pb, useChecksum, tabAddr, ws,
-                               warp, W, lane, outSize);
+      encodeMemberBlocks<WIDE, KIND>(sc, md, m, first, min(nb, first + chunkBlocks), pb, useChecksum, tabAddr, ws,
+                                     warp, W, lane, outSize);
     } else {
       __nanosleep(256);
     }
@@ -1265,8 +1420,8 @@ int smCount() {
 
 struct ScratchPlan {
   size_t members, workIdx, uploadEnd, zeroBegin, hist, histDone, checksum, ticket, allocDone, ready, zeroEnd, lookback,
-      lookbackEnd, table, spill, compRows, total;
-  uint32_t compStride, spillWarps;
+      lookbackEnd, table, spill, total;
+  uint32_t spillWarps;
 };
 
 // Encoder warps that may need a spill slot (one slot = the worst-case stream of one block): never
@@ -1301,8 +1456,6 @@ ScratchPlan planScratch(int kind, uint32_t n, uint32_t maxSize, uint32_t totalTi
   p.table = o; o = alignUp256(o + sizeof(uint4) * kNumSymbols * (size_t)n);
   p.spillWarps = spillWarps;
   p.spill = o; o = alignUp256(o + (size_t)spillWarps * maxBlockWords(11) * 2u);
-  p.compStride = kind == kKindBytes ? 0u : roundUp(maxSize, 16u);
-  p.compRows = o; o = alignUp256(o + (size_t)p.compStride * n);
   p.total = o;
   return p;
 }
@@ -1335,14 +1488,14 @@ HostStage& hostStage() {
   return h;
 }
 
-template <int KIND, bool WIDE>
+template <int KIND, bool WIDE, bool STAGED>
 int launchFused(const EncodeScratch& sc, const uint32_t* histogram_dev, int pb, bool checksum, uint32_t n,
                 uint32_t totalItems, uint32_t totalChunks, uint32_t slabVecs, uint32_t chunkBlocks,
                 uint32_t slotWords, uint32_t statsEvery, uint32_t spillWarps, uint32_t* outSize_dev,
                 cudaStream_t stream) {
-  auto kern = encodeFusedKernel<KIND, WIDE>;
+  auto kern = encodeFusedKernel<KIND, WIDE, STAGED>;
   constexpr uint32_t W = kStatsThreads / 32;
-  const size_t smemBytes = (size_t)W * encFastWarpSmem(slotWords);
+  const size_t smemBytes = (size_t)W * encFastWarpSmem(slotWords, KIND);
   static thread_local int perSm = 0;
   static thread_local size_t perSmKey = 0;
   int devOrdinal = 0;
@@ -1367,6 +1520,56 @@ int launchFused(const EncodeScratch& sc, const uint32_t* histogram_dev, int pb, 
   return DGB_OK;
 }
 
+// K2 of the two-kernel path for one data kind: variant 0 = canonical (ordered, packed table),
+// 1 = fast + packed table, 2 = fast + wide table.  Launch attributes and occupancy are cached per
+// host thread and (variant, shared-memory size, device).
+template <int KIND>
+struct K2Launcher {
+  static int residentPerSm(int variant, uint32_t W, size_t smemBytes, int* out) {
+    static thread_local size_t keySmem = 0;
+    static thread_local uint32_t keyW = 0;
+    static thread_local int keyVariant = -1, keyDev = -1, perSm = 1;
+    int dev = 0;
+    DGB_CUDA_TRY(cudaGetDevice(&dev));
+    if (keySmem != smemBytes || keyW != W || keyVariant != variant || keyDev != dev) {
+      int occ = 0;
+      if (variant == 0) {
+        DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel<KIND>, (int)(W * 32), smemBytes));
+      } else if (variant == 1) {
+        DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast<false, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast<false, KIND>, (int)(W * 32), smemBytes));
+      } else {
+        DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast<true, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast<true, KIND>, (int)(W * 32), smemBytes));
+      }
+      perSm = std::max(occ, 1);
+      keySmem = smemBytes; keyW = W; keyVariant = variant; keyDev = dev;
+    }
+    *out = perSm;
+    return DGB_OK;
+  }
+  static void launch(int variant, uint32_t grid, uint32_t W, size_t smemBytes, cudaStream_t ps, const EncodeScratch& sc,
+                     int pb, bool checksum, uint32_t n, uint32_t totalTickets, uint32_t blockBegin, uint32_t blockEnd,
+                     uint32_t slotWords, uint32_t spillWarpBase, uint32_t* outSize_dev) {
+    if (variant == 0) {
+      encodeKernel<KIND><<<grid, W * 32, smemBytes, ps>>>(sc, pb, checksum, n, totalTickets, outSize_dev);
+    } else if (variant == 1) {
+      encodeKernelFast<false, KIND><<<grid, W * 32, smemBytes, ps>>>(sc, pb, checksum, n, blockBegin, blockEnd, slotWords,
+                                                                    spillWarpBase, outSize_dev);
+    } else {
+      encodeKernelFast<true, KIND><<<grid, W * 32, smemBytes, ps>>>(sc, pb, checksum, n, blockBegin, blockEnd, slotWords,
+                                                                   spillWarpBase, outSize_dev);
+    }
+  }
+};
+
+#define DGB_BY_KIND(kind, CALL)                             \
+  ((kind) == kKindBytes ? K2Launcher<kKindBytes>::CALL      \
+   : (kind) == kKindF16 ? K2Launcher<kKindF16>::CALL        \
+   : (kind) == kKindBF16 ? K2Launcher<kKindBF16>::CALL      \
+                         : K2Launcher<kKindF32>::CALL)
+
 }  // namespace
 
 size_t encodeTempBytes(int kind, uint32_t n, uint32_t maxSize) {
@@ -1387,7 +1590,19 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   const uint32_t elemBytes = kind == kKindF32 ? 4u : (kind == kKindBytes ? 1u : 2u);
   const bool canonical = opt.encode_canonical != 0;
   const bool fused = !canonical && opt.encode_fused != 0;
-  const uint32_t slabVecs = (uint32_t)std::max(1, opt.hist_slab_kb) * 1024u / 16u;
+  // staging slot of the fast / fused encoder (spills to global scratch when a block needs more)
+  uint32_t slotWords = opt.encode_slot_words > 0 ? (uint32_t)opt.encode_slot_words
+                                                 : (kind == kKindBytes ? 2304u : 1536u);
+  slotWords = std::max<uint32_t>(roundUp(slotWords, 8u), kEncGroupRows * 32u + 264u);
+  slotWords = std::min(slotWords, maxBlockWords(pb));
+  // statistics slab: the two-kernel path streams it through registers; the fused launch lands it in
+  // the part of the CTA's dynamic shared memory that the histograms do not use (TMA bulk copy)
+  const bool staged = fused && opt.fused_stage != 0;
+  uint32_t slabVecs = (uint32_t)std::max(1, opt.hist_slab_kb) * 1024u / 16u;
+  if (staged) {
+    const uint32_t stageBytes = (kStatsThreads / 32) * encFastWarpSmem(slotWords, kind) - (uint32_t)sizeof(uint32_t) * kStatsWarps * kNumSymbols;
+    slabVecs = std::max(1u, std::min(slabVecs, stageBytes / 16u));
+  }
   const uint32_t chunkBlocks = (uint32_t)std::max(1, std::min(opt.fused_chunk_blocks, 4096));
   const bool doPass = histogram_dev == nullptr || checksum;
 
@@ -1442,8 +1657,6 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   sc.ready = reinterpret_cast<uint32_t*>(base + sp.ready);
   sc.spill = base + sp.spill;
   sc.table = reinterpret_cast<uint4*>(base + sp.table);
-  sc.compRows = base + sp.compRows;
-  sc.compStride = sp.compStride;
 
   DGB_CUDA_TRY(cudaMemcpyAsync(base + sp.members, hs.upload.data(), hs.upload.size(), cudaMemcpyHostToDevice, stream));
   DGB_CUDA_TRY(cudaMemsetAsync(base + sp.zeroBegin, 0, (canonical ? sp.lookbackEnd : sp.zeroEnd) - sp.zeroBegin, stream));
@@ -1454,19 +1667,15 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
                          (opt.encode_wide_table > 0 || kind == DGB_BFLOAT16 || kind == DGB_FLOAT32);
   sc.wideTable = wideTable;
 
-  // staging slot of the fast / fused encoder (spills to global scratch when a block needs more)
-  uint32_t slotWords = opt.encode_slot_words > 0 ? (uint32_t)opt.encode_slot_words
-                                                 : (kind == kKindBytes ? 2304u : 1536u);
-  slotWords = std::max<uint32_t>(roundUp(slotWords, 8u), kEncGroupRows * 32u + 264u);
-  slotWords = std::min(slotWords, maxBlockWords(pb));
-
   if (fused) {
     // ---- one persistent launch: statistics items and encode chunks from two counters ----
     const uint32_t statsEvery = (uint32_t)std::max(0, opt.fused_stats_every);
     const uint32_t ti = (uint32_t)items, tc = (uint32_t)chunks;
-#define DGB_FUSED(K, WD) \
-  launchFused<K, WD>(sc, histogram_dev, pb, checksum, n, ti, tc, slabVecs, chunkBlocks, slotWords, statsEvery, \
-                     sp.spillWarps, outSize_dev, stream)
+#define DGB_FUSED(K, WD)                                                                                          \
+  (staged ? launchFused<K, WD, true>(sc, histogram_dev, pb, checksum, n, ti, tc, slabVecs, chunkBlocks, slotWords, \
+                                     statsEvery, sp.spillWarps, outSize_dev, stream)                               \
+          : launchFused<K, WD, false>(sc, histogram_dev, pb, checksum, n, ti, tc, slabVecs, chunkBlocks, slotWords, \
+                                      statsEvery, sp.spillWarps, outSize_dev, stream))
     switch (kind) {
       case kKindBytes: return wideTable ? DGB_FUSED(kKindBytes, true) : DGB_FUSED(kKindBytes, false);
       case kKindF16: return wideTable ? DGB_FUSED(kKindF16, true) : DGB_FUSED(kKindF16, false);
@@ -1496,38 +1705,13 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   }
 
   // K2 launch configuration (same for every part)
-  const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb) : encFastWarpSmem(slotWords));
-  // launch attributes and occupancy: cached per host thread, re-done when the kernel variant, its
-  // shared-memory size or the thread's current device changes (function attributes are per device)
-  int devOrdinal = 0;
-  DGB_CUDA_TRY(cudaGetDevice(&devOrdinal));
-  static thread_local int configuredDev = -1;
-  if (configuredDev != devOrdinal) {
-    DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    DGB_CUDA_TRY(cudaFuncSetAttribute(encodeKernelFast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    configuredDev = devOrdinal;
-  }
-  static thread_local size_t occKeySmem = 0;
-  static thread_local uint32_t occKeyW = 0;
-  static thread_local int occKeyVariant = -1, occKeyDev = -1;
-  static thread_local int perSm = 1;
+  const size_t smemBytes = (size_t)W * (canonical ? encWarpSmem(pb, kind) : encFastWarpSmem(slotWords, kind));
   // 0: canonical kernel (packed table), 1: fast kernel + packed table, 2: fast kernel + wide table
   const int variant = canonical ? 0 : (wideTable ? 2 : 1);
-  if (occKeySmem != smemBytes || occKeyW != W || occKeyVariant != variant || occKeyDev != devOrdinal) {
-    int occ = 0;
-    if (variant == 0) {
-      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernel, (int)(W * 32), smemBytes));
-    } else if (variant == 1) {
-      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast<false>, (int)(W * 32), smemBytes));
-    } else {
-      DGB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, encodeKernelFast<true>, (int)(W * 32), smemBytes));
-    }
-    perSm = std::max(occ, 1);
-    occKeySmem = smemBytes;
-    occKeyW = W;
-    occKeyVariant = variant;
-    occKeyDev = devOrdinal;
+  int perSm = 1;
+  {
+    const int rc = DGB_BY_KIND(kind, residentPerSm(variant, W, smemBytes, &perSm));
+    if (rc != DGB_OK) return rc;
   }
   const uint64_t resident = (uint64_t)perSm * sms;
   const uint32_t spillWarpsPerPart = sp.spillWarps / (uint32_t)parts;
@@ -1569,23 +1753,18 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     const uint32_t partBlocks = blockEnd - blockBegin;
     if (partBlocks > 0) {
       timerBegin(kSlotEncode, ps);
+      uint32_t grid2;
       if (canonical) {
-        const uint32_t grid2 = std::min<uint32_t>(divUp(totalTickets, W), (uint32_t)resident);
-        encodeKernel<<<grid2, W * 32, smemBytes, ps>>>(sc, kind, pb, checksum, n, totalTickets, outSize_dev);
+        grid2 = std::min<uint32_t>(divUp(totalTickets, W), (uint32_t)resident);
       } else {
         // one resident wave, equal rounds per warp (see launchDecode)
         const uint64_t rounds = std::max<uint64_t>(1, (partBlocks + resident * W - 1) / (resident * W));
         const uint64_t want = ((uint64_t)partBlocks + W * rounds - 1) / (W * rounds);
-        uint32_t grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
+        grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
         grid2 = std::max(1u, std::min(grid2, spillWarpsPerPart / W));  // every warp owns a spill slot
-        if (wideTable) {
-          encodeKernelFast<true><<<grid2, W * 32, smemBytes, ps>>>(sc, kind, pb, checksum, n, blockBegin, blockEnd, slotWords,
-                                                                 (uint32_t)part * spillWarpsPerPart, outSize_dev);
-        } else {
-          encodeKernelFast<false><<<grid2, W * 32, smemBytes, ps>>>(sc, kind, pb, checksum, n, blockBegin, blockEnd, slotWords,
-                                                                  (uint32_t)part * spillWarpsPerPart, outSize_dev);
-        }
       }
+      DGB_BY_KIND(kind, launch(variant, grid2, W, smemBytes, ps, sc, pb, checksum, n, totalTickets, blockBegin, blockEnd,
+                               slotWords, (uint32_t)part * spillWarpsPerPart, outSize_dev));
       DGB_CUDA_TRY(cudaGetLastError());
       timerEnd(kSlotEncode, ps);
     }

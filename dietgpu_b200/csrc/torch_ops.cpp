@@ -76,20 +76,26 @@ struct Scratch {
 };
 
 // ---- sizes ----------------------------------------------------------------
+// The C ABI reports "worst-case archive exceeds the format's 32-bit sizes" as 0 (the reference
+// CHECK-aborts, ans/GpuANSEncode.cu:22); never size an output tensor from that.
+int64_t bound(uint32_t v) {
+  TORCH_CHECK(v != 0, "dietgpu: input too large for one archive (32-bit format limit)");
+  return (int64_t)v;
+}
 std::tuple<int64_t, int64_t> max_float_compressed_output_size(const std::vector<Tensor>& ts) {
   TORCH_CHECK(!ts.empty());
   auto s = totalAndMax(ts);
-  return {(int64_t)ts.size(), getMaxFloatCompressedSize(floatTypeOf(ts[0]), std::get<1>(s))};
+  return {(int64_t)ts.size(), bound(getMaxFloatCompressedSize(floatTypeOf(ts[0]), std::get<1>(s)))};
 }
 int64_t max_float_compressed_size(const Tensor& dtype, int64_t size) {
-  return getMaxFloatCompressedSize(floatTypeOf(dtype), size);
+  return bound(getMaxFloatCompressedSize(floatTypeOf(dtype), size));
 }
 std::tuple<int64_t, int64_t> max_any_compressed_output_size(const std::vector<Tensor>& ts) {
   TORCH_CHECK(!ts.empty());
   auto s = totalAndMax(ts);
-  return {(int64_t)ts.size(), getMaxCompressedSize(std::get<1>(s) * ts[0].element_size())};
+  return {(int64_t)ts.size(), bound(getMaxCompressedSize(std::get<1>(s) * ts[0].element_size()))};
 }
-int64_t max_any_compressed_size(int64_t bytes) { return getMaxCompressedSize(bytes); }
+int64_t max_any_compressed_size(int64_t bytes) { return bound(getMaxCompressedSize(bytes)); }
 
 // ---- compress ---------------------------------------------------------------
 void validateOut(const std::optional<Tensor>& outCompressed, const std::optional<Tensor>& outSizes, int64_t n,

@@ -75,22 +75,29 @@ class _Temp:
 
 # ---------------------------------------------------------------- sizes ----
 
+def _bound(v: int, size: int) -> int:
+    """The C ABI returns 0 when the worst-case archive does not fit the format's 32-bit sizes (the
+    reference CHECK-aborts there, ans/GpuANSEncode.cu:22): raise instead of sizing a buffer from 0."""
+    _check(v != 0 or size == 0, f"input of {size} elements is too large for one archive (32-bit format limit)")
+    return v
+
+
 def max_float_compressed_output_size(ts: Sequence[torch.Tensor]) -> Tuple[int, int]:
     _, mx = _total_and_max(ts)
-    return len(ts), capi.lib().dgb_float_max_compressed_size(_float_type(ts[0]), mx)
+    return len(ts), _bound(capi.lib().dgb_float_max_compressed_size(_float_type(ts[0]), mx), mx)
 
 
 def max_float_compressed_size(dtype: torch.Tensor, size: int) -> int:
-    return capi.lib().dgb_float_max_compressed_size(_float_type(dtype), size)
+    return _bound(capi.lib().dgb_float_max_compressed_size(_float_type(dtype), size), size)
 
 
 def max_any_compressed_output_size(ts: Sequence[torch.Tensor]) -> Tuple[int, int]:
     _, mx = _total_and_max(ts)
-    return len(ts), capi.lib().dgb_ans_max_compressed_size(mx * ts[0].element_size())
+    return len(ts), _bound(capi.lib().dgb_ans_max_compressed_size(mx * ts[0].element_size()), mx)
 
 
 def max_any_compressed_size(nbytes: int) -> int:
-    return capi.lib().dgb_ans_max_compressed_size(nbytes)
+    return _bound(capi.lib().dgb_ans_max_compressed_size(nbytes), nbytes)
 
 
 # ------------------------------------------------------------- compress ----
@@ -177,7 +184,7 @@ def compress_data_split_size(compress_as_float: bool, t_in: torch.Tensor, t_in_s
             _check(s % 4 == 0, "the size of an interior split is not a multiple of 4 bytes")
     mx = max(splits)
     L = capi.lib()
-    cols = L.dgb_float_max_compressed_size(ft, mx) if compress_as_float else L.dgb_ans_max_compressed_size(mx)
+    cols = _bound(L.dgb_float_max_compressed_size(ft, mx) if compress_as_float else L.dgb_ans_max_compressed_size(mx), mx)
     comp, sizes = _validate_out(out_compressed, out_compressed_bytes, n, cols, dev)
     arr = capi.u32_array(splits)
     with torch.cuda.device(dev):

@@ -180,6 +180,15 @@ int dgb_float_get_compressed_info(void* temp_dev, size_t temp_bytes, const void*
                                   uint32_t* out_sizes_dev, uint32_t* out_types_dev,
                                   uint32_t* out_checksum_dev, void* stream);
 
+/* ---- host front end helpers (new) ----------------------------------------- */
+/* Plain asynchronous copies on `stream`, used by the host-buffer front end (dietgpu_b200.HostCodec)
+ * to move whole member groups in one DMA each instead of one call per member.  dgb_copy_async is
+ * cudaMemcpyAsync(cudaMemcpyDefault); dgb_copy_rows_async copies `rows` rows of `width_bytes` between
+ * two pitched matrices (cudaMemcpy2DAsync), e.g. archives [n, cols] device <-> pinned host. */
+int dgb_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+int dgb_copy_rows_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                        size_t width_bytes, size_t rows, void* stream);
+
 /* ---- tuning knob (benchmarks / tests only) ------------------------------- */
 /* Selects an internal kernel variant by name ("decode_stage", "hist_mode" ...).
  * Unknown names return DGB_ERR_INVALID_ARG.  Defaults are the tuned choice. */

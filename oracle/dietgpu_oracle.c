@@ -434,6 +434,268 @@ int dgo_float_decompress(int ft, const uint8_t* in, int pb, int verify_checksum,
   return DGO_OK;
 }
 
+/* ------------------------------------------------ whole-batch CPU baseline -- */
+
+/*
+ * The host-CPU baseline of bench.py: one call takes the WHOLE batch and spreads every phase over
+ * all cores -- split + histogram over (member, slab) pairs, normalisation over members, block
+ * coding over the flat list of 4 KiB blocks of all members, packing over members; decode likewise
+ * (LUTs over members, blocks over the flat list, join over (member, slab) pairs).  Same algorithm
+ * and same archives as dgo_ans_encode / dgo_float_compress above (tests/test_oracle.py compares
+ * them byte for byte); the block coder divides with the reference's reciprocal
+ * (ans/GpuANSStatistics.cuh:343-358 + ans/GpuANSEncode.cuh:79-86) instead of a hardware divide.
+ * ft: 0 = raw bytes, else DGO_F16 / DGO_BF16 / DGO_F32.  sizes in bytes (ft 0) or float words.
+ * t_sec[0] / t_sec[1] receive the wall time of the encode / decode phase.
+ * Returns DGO_OK, or the first decode error.
+ */
+#define DGO_SLAB 65536u
+
+static uint32_t encode_block_magic(const uint8_t* in, uint32_t n, int pb, const uint32_t* tab /* [256][4] */,
+                                   uint32_t state[DGO_LANES], uint16_t* w) {
+  const uint32_t K = 1u << pb;
+  uint32_t cnt = 0;
+  for (uint32_t l = 0; l < DGO_LANES; ++l) state[l] = DGO_STATE_MIN;
+  for (uint32_t r = 0; r < n; r += DGO_LANES) {
+    uint32_t lanes = n - r < DGO_LANES ? n - r : DGO_LANES;
+    for (uint32_t l = 0; l < lanes; ++l) {
+      const uint32_t* e = tab + 4u * in[r + l]; /* {pdf, cdf, magic, shift} */
+      uint32_t x = state[l];
+      if (x >= (e[0] << (31 - pb))) {
+        w[cnt++] = (uint16_t)(x & 0xffffu);
+        x >>= 16;
+      }
+      uint32_t t = (uint32_t)(((uint64_t)x * e[2]) >> 32);
+      uint32_t div = (uint32_t)(((uint64_t)t + x) >> e[3]); /* ans/GpuANSEncode.cuh:79-86 */
+      state[l] = div * K + (x - div * e[0]) + e[1];
+    }
+  }
+  return cnt;
+}
+
+void dgo_div_magic(uint32_t pdf, uint32_t* magic, uint32_t* shift);
+
+int dgo_batch_roundtrip(int ft, const void* const* in, const uint32_t* sizes, uint32_t n, int pb,
+                        uint8_t* const* archives, uint32_t* archive_sizes, void* const* outs,
+                        double* t_sec) {
+  const uint32_t wb = ft == DGO_F32 ? 4u : (ft == 0 ? 1u : 2u);
+  const uint32_t slot_words = DGO_BLOCK * 11u / 16u + 8u;
+  /* flat indices: blocks and slabs of every member */
+  uint64_t* blk0 = (uint64_t*)malloc(sizeof(uint64_t) * (n + 1));
+  uint64_t* slab0 = (uint64_t*)malloc(sizeof(uint64_t) * (n + 1));
+  blk0[0] = slab0[0] = 0;
+  for (uint32_t m = 0; m < n; ++m) {
+    blk0[m + 1] = blk0[m] + div_up(sizes[m], DGO_BLOCK);
+    slab0[m + 1] = slab0[m] + (sizes[m] ? div_up(sizes[m], DGO_SLAB) : 0u);
+  }
+  const uint64_t nblocks = blk0[n], nslabs = slab0[n];
+  uint32_t* blk_member = (uint32_t*)malloc(sizeof(uint32_t) * (nblocks ? nblocks : 1));
+  uint32_t* slab_member = (uint32_t*)malloc(sizeof(uint32_t) * (nslabs ? nslabs : 1));
+  for (uint32_t m = 0; m < n; ++m) {
+    for (uint64_t b = blk0[m]; b < blk0[m + 1]; ++b) blk_member[b] = m;
+    for (uint64_t s = slab0[m]; s < slab0[m + 1]; ++s) slab_member[s] = m;
+  }
+  uint32_t* hist = (uint32_t*)calloc((size_t)n * 256u, sizeof(uint32_t));
+  uint32_t* tab = (uint32_t*)malloc((size_t)n * 1024u * sizeof(uint32_t));
+  uint32_t* luts = (uint32_t*)malloc(((size_t)n << pb) * sizeof(uint32_t));
+  uint16_t* slots = (uint16_t*)malloc((size_t)(nblocks ? nblocks : 1) * slot_words * 2u);
+  uint32_t* words = (uint32_t*)malloc(sizeof(uint32_t) * (nblocks ? nblocks : 1));
+  uint8_t** comp = (uint8_t**)malloc(sizeof(uint8_t*) * n);
+  for (uint32_t m = 0; m < n; ++m)
+    comp[m] = ft ? (uint8_t*)malloc(sizes[m] ? sizes[m] : 1) : (uint8_t*)in[m];
+  int err = DGO_OK;
+#ifdef _OPENMP
+  double t0 = omp_get_wtime();
+#else
+  double t0 = 0;
+#endif
+
+  /* ---------------- encode ---------------- */
+#pragma omp parallel
+  {
+    /* split + histogram, one slab of one member per task */
+#pragma omp for schedule(dynamic, 4)
+    for (int64_t s = 0; s < (int64_t)nslabs; ++s) {
+      const uint32_t m = slab_member[s];
+      const uint32_t e0 = (uint32_t)((uint64_t)s - slab0[m]) * DGO_SLAB;
+      const uint32_t e1 = sizes[m] - e0 < DGO_SLAB ? sizes[m] : e0 + DGO_SLAB;
+      uint32_t local[256];
+      memset(local, 0, sizeof(local));
+      uint8_t* c = comp[m];
+      if (ft == 0) {
+        for (uint32_t i = e0; i < e1; ++i) local[c[i]]++;
+      } else {
+        uint8_t* non = archives[m] + 16;
+        if (ft == DGO_F32) {
+          const uint32_t* w = (const uint32_t*)in[m];
+          uint8_t* non1 = non + 2u * round_up(sizes[m], 8u);
+          for (uint32_t i = e0; i < e1; ++i) {
+            uint32_t v = rotl32(w[i], 1);
+            c[i] = (uint8_t)(v >> 24);
+            put16(non + 2u * i, (uint16_t)(v & 0xffffu));
+            non1[i] = (uint8_t)((v >> 16) & 0xffu);
+            local[c[i]]++;
+          }
+        } else {
+          const uint16_t* w = (const uint16_t*)in[m];
+          for (uint32_t i = e0; i < e1; ++i) {
+            split16(ft, w[i], &c[i], &non[i]);
+            local[c[i]]++;
+          }
+        }
+      }
+      for (uint32_t k = 0; k < 256; ++k)
+        if (local[k]) {
+#pragma omp atomic
+          hist[(size_t)m * 256u + k] += local[k];
+        }
+    }
+    /* per member: normalise, encoder table {pdf, cdf, magic, shift}, pdf + float header into the archive */
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t m = 0; m < (int64_t)n; ++m) {
+      uint32_t pdf[256], cdf[256];
+      dgo_normalize(hist + (size_t)m * 256u, sizes[m], pb, pdf);
+      cdf_from_pdf(pdf, cdf);
+      uint32_t* t = tab + (size_t)m * 1024u;
+      for (uint32_t k = 0; k < 256; ++k) {
+        t[4 * k] = pdf[k];
+        t[4 * k + 1] = cdf[k];
+        dgo_div_magic(pdf[k], &t[4 * k + 2], &t[4 * k + 3]);
+      }
+      uint8_t* a = archives[m];
+      if (ft) {
+        const uint32_t ncb = dgo_float_noncomp_bytes(ft, sizes[m]);
+        put32(a + 0, (DGO_FLOAT_MAGIC << 16) | DGO_VERSION);
+        put32(a + 4, sizes[m]);
+        put32(a + 8, (uint32_t)ft);
+        put32(a + 12, 0);
+        /* zero padding of the stored planes */
+        if (ft == DGO_F32) {
+          memset(a + 16 + 2u * sizes[m], 0, 2u * round_up(sizes[m], 8u) - 2u * sizes[m]);
+          memset(a + 16 + 2u * round_up(sizes[m], 8u) + sizes[m], 0, round_up(sizes[m], 16u) - sizes[m]);
+        } else {
+          memset(a + 16 + sizes[m], 0, ncb - sizes[m]);
+        }
+        a += 16 + ncb;
+      }
+      for (uint32_t k = 0; k < 256; ++k) put16(a + 32 + 2 * k, (uint16_t)pdf[k]);
+    }
+    /* every 4 KiB block of every member */
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t b = 0; b < (int64_t)nblocks; ++b) {
+      const uint32_t m = blk_member[b];
+      const uint32_t blk = (uint32_t)((uint64_t)b - blk0[m]);
+      const uint32_t nb = (uint32_t)(blk0[m + 1] - blk0[m]);
+      const uint32_t start = blk * DGO_BLOCK;
+      const uint32_t len = sizes[m] - start < DGO_BLOCK ? sizes[m] - start : DGO_BLOCK;
+      uint32_t st[DGO_LANES];
+      words[b] = encode_block_magic(comp[m] + start, len, pb, tab + (size_t)m * 1024u, st, slots + (size_t)b * slot_words);
+      uint8_t* a = archives[m] + (ft ? 16u + dgo_float_noncomp_bytes(ft, sizes[m]) : 0u);
+      memcpy(a + 32 + 512 + 128u * blk, st, 128);
+      (void)nb;
+    }
+    /* per member: scan of padded sizes, pack, header */
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t m = 0; m < (int64_t)n; ++m) {
+      const uint32_t nb = (uint32_t)(blk0[m + 1] - blk0[m]);
+      const uint32_t extra = ft ? 16u + dgo_float_noncomp_bytes(ft, sizes[m]) : 0u;
+      uint8_t* a = archives[m] + extra;
+      uint8_t* p_bw = a + 32 + 512 + 128u * nb;
+      uint8_t* p_data = p_bw + 8u * round_up(nb, 2u);
+      if (nb & 1u) memset(p_bw + 8u * nb, 0, 8);
+      uint32_t off = 0;
+      for (uint32_t k = 0; k < nb; ++k) {
+        const uint64_t b = blk0[m] + k;
+        const uint32_t len = sizes[m] - k * DGO_BLOCK < DGO_BLOCK ? sizes[m] - k * DGO_BLOCK : DGO_BLOCK;
+        put32(p_bw + 8u * k, (len << 16) | words[b]);
+        put32(p_bw + 8u * k + 4, off);
+        const uint32_t padded = round_up(words[b], 8u);
+        memcpy(p_data + 2u * off, slots + (size_t)b * slot_words, 2u * words[b]);
+        memset(p_data + 2u * (off + words[b]), 0, 2u * (padded - words[b]));
+        off += padded;
+      }
+      put32(a + 0, (DGO_ANS_MAGIC << 16) | DGO_VERSION);
+      put32(a + 4, nb);
+      put32(a + 8, sizes[m]);
+      put32(a + 12, off);
+      put32(a + 16, (uint32_t)pb);
+      put32(a + 20, 0);
+      put32(a + 24, 0);
+      put32(a + 28, 0);
+      archive_sizes[m] = extra + dgo_ans_overhead(nb) + 2u * off;
+    }
+  }
+#ifdef _OPENMP
+  double t1 = omp_get_wtime();
+#else
+  double t1 = 0;
+#endif
+
+  /* ---------------- decode ---------------- */
+#pragma omp parallel
+  {
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t m = 0; m < (int64_t)n; ++m) {
+      const uint8_t* a = archives[m] + (ft ? 16u + dgo_float_noncomp_bytes(ft, sizes[m]) : 0u);
+      if (sizes[m] && build_decode_lut(a + 32, pb, luts + ((size_t)m << pb)) != DGO_OK) {
+#pragma omp atomic write
+        err = DGO_ERR_CORRUPT;
+      }
+    }
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t b = 0; b < (int64_t)nblocks; ++b) {
+      const uint32_t m = blk_member[b];
+      const uint32_t blk = (uint32_t)((uint64_t)b - blk0[m]);
+      const uint32_t nb = (uint32_t)(blk0[m + 1] - blk0[m]);
+      const uint8_t* a = archives[m] + (ft ? 16u + dgo_float_noncomp_bytes(ft, sizes[m]) : 0u);
+      const uint8_t* p_states = a + 32 + 512;
+      const uint8_t* p_bw = p_states + 128u * nb;
+      const uint8_t* p_data = p_bw + 8u * round_up(nb, 2u);
+      uint32_t st[DGO_LANES];
+      const uint32_t bw = get32(p_bw + 8u * blk), off = get32(p_bw + 8u * blk + 4);
+      memcpy(st, p_states + 128u * blk, 128);
+      uint8_t* dst = ft ? comp[m] : (uint8_t*)outs[m];
+      int r = decode_block(st, (const uint16_t*)(p_data + 2u * (size_t)off), bw & 0xffffu, bw >> 16, pb,
+                           luts + ((size_t)m << pb), dst + (size_t)blk * DGO_BLOCK);
+      if (r != DGO_OK) {
+#pragma omp atomic write
+        err = r;
+      }
+    }
+    if (ft) {
+#pragma omp for schedule(dynamic, 4)
+      for (int64_t s = 0; s < (int64_t)nslabs; ++s) {
+        const uint32_t m = slab_member[s];
+        const uint32_t e0 = (uint32_t)((uint64_t)s - slab0[m]) * DGO_SLAB;
+        const uint32_t e1 = sizes[m] - e0 < DGO_SLAB ? sizes[m] : e0 + DGO_SLAB;
+        const uint8_t* non = archives[m] + 16;
+        const uint8_t* c = comp[m];
+        if (ft == DGO_F32) {
+          uint32_t* w = (uint32_t*)outs[m];
+          const uint8_t* non1 = non + 2u * round_up(sizes[m], 8u);
+          for (uint32_t i = e0; i < e1; ++i) {
+            uint32_t v = ((uint32_t)c[i] << 24) | ((uint32_t)non1[i] << 16) | get16(non + 2u * i);
+            w[i] = rotr32(v, 1);
+          }
+        } else {
+          uint16_t* w = (uint16_t*)outs[m];
+          for (uint32_t i = e0; i < e1; ++i) w[i] = join16(ft, c[i], non[i]);
+        }
+      }
+    }
+  }
+#ifdef _OPENMP
+  double t2 = omp_get_wtime();
+#else
+  double t2 = 0;
+#endif
+  if (t_sec) { t_sec[0] = t1 - t0; t_sec[1] = t2 - t1; }
+  if (ft) for (uint32_t m = 0; m < n; ++m) free(comp[m]);
+  free(comp); free(words); free(slots); free(luts); free(tab); free(hist);
+  free(slab_member); free(blk_member); free(slab0); free(blk0);
+  (void)wb;
+  return err;
+}
+
 /* --------------------------------------------------------------- extras -- */
 
 /* Exposed for tests: the encoder division constants of

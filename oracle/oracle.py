@@ -60,6 +60,8 @@ def lib():
         L.dgo_float_decompress.restype = i32
         L.dgo_float_decompress.argtypes = [i32, vp, i32, i32, vp, u32, vp]
         L.dgo_div_magic.argtypes = [u32, vp, vp]
+        L.dgo_batch_roundtrip.restype = i32
+        L.dgo_batch_roundtrip.argtypes = [i32, vp, vp, u32, i32, vp, vp, vp, vp]
         L.dgo_num_threads.restype = i32
         L.dgo_set_threads.argtypes = [i32]
         _lib = L
@@ -170,6 +172,27 @@ def float_decompress(ft: int, arch, pb: int = 10, capacity: int | None = None,
     got = C.c_uint32()
     rc = lib().dgo_float_decompress(ft, _ptr(a), pb, int(verify_checksum), _ptr(out), cap, C.byref(got))
     return rc, out[:min(cap, got.value)].copy(), got.value
+
+
+def batch_roundtrip(ft: int, arrays, pb: int = 10):
+    """Whole-batch encode then decode with every phase spread over all host cores (the CPU baseline
+    of bench.py).  ft: 0 = raw bytes (uint8 arrays), else F16/BF16 (uint16 arrays) / F32 (uint32).
+    Returns (archives, decoded arrays, encode seconds, decode seconds)."""
+    n = len(arrays)
+    arrs = [np.ascontiguousarray(a) for a in arrays]
+    sizes = np.array([a.size for a in arrs], dtype=np.uint32)
+    caps = [float_max_compressed_size(ft, int(k)) if ft else ans_max_compressed_size(int(k)) for k in sizes]
+    archs = [np.empty(c, dtype=np.uint8) for c in caps]
+    outs = [np.empty_like(a) for a in arrs]
+    P = C.c_void_p * n
+    in_p = P(*[a.ctypes.data for a in arrs])
+    ar_p = P(*[a.ctypes.data for a in archs])
+    out_p = P(*[a.ctypes.data for a in outs])
+    asz = np.zeros(n, dtype=np.uint32)
+    t = (C.c_double * 2)()
+    rc = lib().dgo_batch_roundtrip(ft, in_p, _ptr(sizes), n, pb, ar_p, _ptr(asz), out_p, t)
+    assert rc == 0, f"dgo_batch_roundtrip: error {rc}"
+    return [a[:int(k)] for a, k in zip(archs, asz)], outs, t[0], t[1]
 
 
 def num_threads() -> int:

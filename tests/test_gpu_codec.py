@@ -466,16 +466,16 @@ def test_kernel_variants_agree():
 
     a = [zipf_bytes(300000, 1.1, 5), exp_bytes(4097, 50, 6), zipf_bytes(1, 1.0, 7), np.zeros(0, np.uint8)]
     f = [normal_words(50000 + 13 * i, "bf16", i) for i in range(5)]
-    names = ("encode_fused", "decode_fused", "fused_chunk_blocks", "decode_chunk_blocks", "fused_stats_every",
+    names = ("encode_fused", "decode_fused", "fused_chunk_blocks", "fused_stats_every", "fused_stage",
              "encode_warps", "encode_canonical")
     defaults = {k: capi.get_option(k) for k in names}
     variants = [
         dict(encode_fused=0, decode_fused=0),
         dict(encode_fused=1, decode_fused=0),
         dict(encode_fused=0, decode_fused=1),
-        dict(fused_chunk_blocks=1, decode_chunk_blocks=1),
-        dict(fused_chunk_blocks=3, decode_chunk_blocks=5),
-        dict(fused_chunk_blocks=64, decode_chunk_blocks=64),
+        dict(fused_chunk_blocks=1),
+        dict(fused_chunk_blocks=3, fused_stage=0),
+        dict(fused_chunk_blocks=64),
         dict(fused_stats_every=0),
         dict(fused_stats_every=1),
         dict(encode_fused=0, encode_warps=2),
@@ -492,3 +492,77 @@ def test_kernel_variants_agree():
     finally:
         for k, d in defaults.items():
             capi.set_option(k, d)
+
+
+def test_get_compressed_info_matches_oracle():
+    # dgb_{ans,float}_get_compressed_info (ans/GpuANSInfo.cu:14-49, float/GpuFloatInfo.cu:17-64) against
+    # dgo_ans_info / dgo_float_info on the same archives: uncompressed sizes, float types, stored checksums
+    import ctypes as C
+
+    from dietgpu_b200 import capi
+
+    L = capi.lib()
+    arrays = [zipf_bytes(50000 + 977 * i, 1.2, i) for i in range(5)] + [np.zeros(0, np.uint8)]
+    ts = [to_dev_bytes(a) for a in arrays]
+    comp, sizes, _ = dg().compress_data(False, ts, True)
+    hs = sizes.cpu().tolist()
+    n = len(ts)
+    ptrs = capi.ptr_array([comp[i].data_ptr() for i in range(n)])
+    o_sz = torch.zeros(n, dtype=torch.int32, device="cuda")
+    o_ck = torch.zeros(n, dtype=torch.int32, device="cuda")
+    tmp = torch.empty(8 * n + 512, dtype=torch.uint8, device="cuda")
+    tp = tmp.data_ptr() + (-tmp.data_ptr()) % 256
+    capi.check(L.dgb_ans_get_compressed_info(tp, 8 * n + 256, ptrs, 0, n, o_sz.data_ptr(), o_ck.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "ans info")
+    for i in range(n):
+        info = O.ans_info(comp[i, :hs[i]].cpu().numpy())
+        assert info["rc"] == O.OK and info["size"] == hs[i]
+        assert o_sz[i].item() == info["uncompressed"] == arrays[i].size
+        assert (o_ck[i].item() & 0xffffffff) == info["checksum"] == O.ans_info(O.ans_encode(arrays[i], 10, True))["checksum"]
+    # the device-array form returns the same
+    dptrs = torch.tensor([comp[i].data_ptr() for i in range(n)], dtype=torch.int64, device="cuda")
+    o_sz2 = torch.zeros_like(o_sz)
+    capi.check(L.dgb_ans_get_compressed_info(None, 0, C.c_void_p(dptrs.data_ptr()), 1, n, o_sz2.data_ptr(), None,
+                                             torch.cuda.current_stream().cuda_stream), "ans info (device array)")
+    assert torch.equal(o_sz, o_sz2)
+
+    for kind, (ft, _, _) in KINDS.items():
+        words = [normal_words(30000 + 501 * i, kind, i) for i in range(4)]
+        fts = [words_to_tensor(w, kind) for w in words]
+        comp, sizes, _ = dg().compress_data(True, fts, True)
+        hs = sizes.cpu().tolist()
+        n = len(fts)
+        ptrs = capi.ptr_array([comp[i].data_ptr() for i in range(n)])
+        o_sz = torch.zeros(n, dtype=torch.int32, device="cuda")
+        o_ty = torch.zeros(n, dtype=torch.int32, device="cuda")
+        o_ck = torch.zeros(n, dtype=torch.int32, device="cuda")
+        capi.check(L.dgb_float_get_compressed_info(tp, 8 * n + 256, ptrs, 0, n, o_sz.data_ptr(), o_ty.data_ptr(),
+                                                   o_ck.data_ptr(), torch.cuda.current_stream().cuda_stream), "float info")
+        for i in range(n):
+            info = O.float_info(comp[i, :hs[i]].cpu().numpy())
+            assert info["rc"] == O.OK
+            assert o_sz[i].item() == info["size"] == words[i].size
+            assert o_ty[i].item() == info["float_type"] == ft
+            assert (o_ck[i].item() & 0xffffffff) == info["checksum"] == O.float_info(O.float_compress(ft, words[i], 10, True))["checksum"]
+
+
+@pytest.mark.parametrize("kind", ["f16", "bf16", "f32"])
+def test_float_members_not_16_byte_aligned(kind):
+    # split sizes that push every following member off the 16 B grid (dgb_float_compress_split_size lays
+    # members back to back): the statistics pass peels a scalar head and keeps its vector body, and the
+    # planes are written at shifted offsets -- archives must still equal the oracle's
+    ft, tdt, _ = KINDS[kind]
+    sizes = [40003, 8191, 65537, 5, 33001, 12345]
+    words = [normal_words(n, kind, i) for i, n in enumerate(sizes)]
+    big = words_to_tensor(np.concatenate(words), kind)
+    comps, csz, _ = dg().compress_data_split_size(True, big, torch.tensor(sizes, dtype=torch.int32))
+    hs = csz.cpu().tolist()
+    for i, w in enumerate(words):
+        want = O.float_compress(ft, w, 10)
+        assert hs[i] == want.size
+        O.assert_same_float(comps[i][:hs[i]].cpu().numpy(), want, ft, f"member {i}")
+    out = torch.empty_like(big)
+    dg().decompress_data_split_size(True, [comps[i][:hs[i]] for i in range(len(sizes))], out,
+                                    torch.tensor(sizes, dtype=torch.int32))
+    idt = torch.int32 if kind == "f32" else torch.int16
+    assert torch.equal(out.view(idt), big.view(idt))

@@ -159,3 +159,26 @@ def test_threaded_oracle_is_deterministic():
     O.set_threads(max(2, O.num_threads()))
     b = O.ans_encode(d, 10)
     assert np.array_equal(a, b)
+
+
+def test_batch_baseline_equals_per_member_oracle():
+    # the whole-batch multi-core entry (bench.py cpu_baseline) writes the same archives, byte for
+    # byte, as the per-member restatement, and round-trips
+    rng = np.random.default_rng(11)
+    byte_batch = [zipf_bytes(70001, 1.0, 1), zipf_bytes(4096, 1.5, 2), np.zeros(0, np.uint8), zipf_bytes(1, 1.0, 3),
+                  rng.integers(0, 256, 200000, dtype=np.uint8)]
+    for pb in (9, 10, 11):
+        archs, outs, _, _ = O.batch_roundtrip(0, byte_batch, pb)
+        for a, o, d in zip(archs, outs, byte_batch):
+            assert np.array_equal(a, O.ans_encode(d, pb)), pb
+            assert np.array_equal(o, d)
+    for ft, dt in ((O.BF16, np.uint16), (O.F16, np.uint16), (O.F32, np.uint32)):
+        batch = [rng.integers(0, np.iinfo(dt).max, n, dtype=dt) for n in (100003, 4096, 1, 0, 65536)]
+        # concentrate the coded byte so that the archives actually compress
+        for b in batch:
+            if b.size:
+                b[::2] = b[0]
+        archs, outs, _, _ = O.batch_roundtrip(ft, batch, 10)
+        for a, o, d in zip(archs, outs, batch):
+            assert np.array_equal(a, O.float_compress(ft, d, 10)), ft
+            assert np.array_equal(o, d)

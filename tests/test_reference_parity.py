@@ -118,4 +118,10 @@ def test_max_sizes_match_reference():
     for n in (0, 1, 4095, 4096, 4097, 1 << 20, 4 << 20, 123456789, 0x7fffffff // 2):
         assert L.dgb_ans_max_compressed_size(n) == R.ref_ans_max_compressed_size(n)
         for ft in (1, 2, 3):
-            assert L.dgb_float_max_compressed_size(ft, n) == R.ref_float_max_compressed_size(ft, n)
+            mine = L.dgb_float_max_compressed_size(ft, n)
+            if mine == 0:
+                # the exact bound does not fit 32 bits: the reference returns the wrapped sum, this ABI
+                # reports "too large" (0) instead of a value a caller would under-allocate from
+                assert 16 + L.dgb_ans_max_compressed_size(n) + (3 if ft == 3 else 1) * n > 0xffffffff
+                continue
+            assert mine == R.ref_float_max_compressed_size(ft, n)
