@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "../../include/dietgpu_b200_device.cuh"
 
 namespace dgb {
 
@@ -84,70 +85,12 @@ struct EncodeScratch {
 __device__ void normalizeAndPublish(const uint32_t* __restrict__ histGlobal, uint32_t total,
                                     int pb, bool wideTable, uint4* __restrict__ tableOut,
                                     uint8_t* __restrict__ ansArchive) {
-  __shared__ uint32_t sKey[kNumSymbols];
-  __shared__ uint32_t sQByRank[kNumSymbols];
-  __shared__ uint32_t sSymByRank[kNumSymbols];
-  __shared__ uint32_t sPdf[kNumSymbols];
-  __shared__ uint32_t sWarp[kStatsWarps];
-
   const uint32_t t = threadIdx.x;
   const uint32_t K = 1u << pb;
-  const uint32_t count = __ldcg(histGlobal + t);
-
-  // :215-218 fp32 quantisation, IEEE divide, truncation
-  float ratio = __fdiv_rn(__uint2float_rn(count), __uint2float_rn(total));
-  uint32_t q = __float2uint_rz(__fmul_rn((float)K, ratio));
-  if (count > 0 && q == 0) q = 1;
-
-  // sum of q over the block
-  uint32_t incl = q;
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) incl += __shfl_xor_sync(0xffffffffu, incl, d);
-  if ((t & 31) == 0) sWarp[t >> 5] = incl;
-  const uint32_t key = (q << 16) | t;
-  sKey[t] = key;
-  __syncthreads();
-  int sum = 0;
-#pragma unroll
-  for (int w = 0; w < kStatsWarps; ++w) sum += (int)sWarp[w];
-
-  // rank = number of keys strictly greater (descending order, keys unique)
-  uint32_t rank = 0;
-#pragma unroll 8
-  for (int j = 0; j < (int)kNumSymbols; ++j) rank += (sKey[j] > key);
-  sQByRank[rank] = q;
-  sSymByRank[rank] = t;
-  __syncthreads();
-
-  // from here thread t owns RANK t
-  uint32_t qr = sQByRank[t];
-  const uint32_t symr = sSymByRank[t];
-  int diff = (int)K - sum;
-  if (diff > 0) {
-    // :258-273: +1 to every entry whose SYMBOL ID < min(diff, 256), repeated
-    while (diff > 0) {
-      int it = diff < (int)kNumSymbols ? diff : (int)kNumSymbols;
-      if ((int)symr < it) qr += 1;
-      diff -= it;
-    }
-  } else if (diff < 0) {
-    // :274-315: -1 from the smallest entries still > 1, by rank, iterated
-    diff = -diff;
-    while (diff > 0) {
-      int g = __syncthreads_count(qr > 1);
-      int it = diff < g ? diff : g;
-      if (it <= 0) break;
-      if ((int)t >= g - it && (int)t < g) qr -= 1;
-      diff -= it;
-    }
-  }
-  sPdf[symr] = qr;
-  __syncthreads();
-
-  // back to thread t == symbol t
-  const uint32_t pdf = sPdf[t];
-  uint32_t totalPdf;
-  const uint32_t cdf = blockExclusiveScan<kStatsThreads>(pdf, sWarp, &totalPdf);
+  // the normalisation itself is the device-level API's routine (include/dietgpu_b200_device.cuh): one
+  // implementation of the reference's quirks for the library and for user kernels
+  uint32_t cdf;
+  const uint32_t pdf = dietgpu_b200::device::blockNormalizedPdf(__ldcg(histGlobal + t), total, pb, &cdf);
 
   // Division constants.  The reference (:343-358) uses the round-up magic that needs
   // hi32(x * magic) + x; the coder state is always < 2^31 here, so the plain round-up
@@ -895,11 +838,12 @@ __device__ __forceinline__ void spillOut(Spill& sp, uint32_t stageAddr, uint16_t
 // `stageAddr` (spilling to sp.area when the slot is small); float kinds also write the block's
 // stored plane(s).  Returns the TOTAL word count; the words not yet spilled are
 // stage[0 .. total - sp.spilled).
-template <bool WIDE, int KIND>
+template <bool WIDE, int KIND, bool TMA>
 __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ in, uint32_t n, uint32_t elem0,
                                                     const StoredPlanes& planes, uint32_t tabAddr, int pb,
                                                     uint32_t stageAddr, uint16_t* stage, Spill& sp,
-                                                    uint32_t ringAddr, uint32_t lane, uint32_t& stateOut) {
+                                                    uint32_t ringAddr, uint32_t lane, uint32_t& stateOut,
+                                                    uint32_t ringBar = 0, uint32_t* ringPhase = nullptr) {
   typedef EncIn<KIND> In;
   constexpr int U = kEncGroupRows;
   constexpr uint32_t WB = In::kWordBytes;
@@ -913,31 +857,59 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
   uint32_t r = 0;
   sp.spilled = 0;
   if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
-    // input rows stream through the cp.async ring, two groups ahead of the encoder
     const uint32_t groups = fullRows / U;
-    const uint8_t* src = in + lane * 16u;
-    const uint32_t dst = ringAddr + lane * 16u;
-    auto issue = [&](uint32_t g, uint32_t slot) {
+    if (TMA) {
+      // input rows arrive by TMA bulk copies (cp.async.bulk, one instruction of one lane per group of
+      // 16 rows) into a ring of slots, each with its own mbarrier, two groups ahead of the coder
+      auto issue = [&](uint32_t g, uint32_t slot) {
+        if (lane == 0) {
+          mbarExpectTx(ringBar + 8u * slot, kGroupBytes);
+          bulkLoad(ringAddr + slot * kGroupBytes, in + (size_t)g * kGroupBytes, kGroupBytes, ringBar + 8u * slot);
+        }
+      };
+      if (lane == 0) fenceProxyAsync();  // the ring was last touched through the generic proxy
+      if (groups > 0) issue(0, 0);
+      if (groups > 1) issue(1, 1);
+      uint32_t slot = 0, slotNext = 2 % In::kRingSlots, phases = *ringPhase;
+      for (uint32_t k = 0; k < groups; ++k) {
+        __syncwarp();  // every lane is done with the group that last sat in slotNext
+        if (k + 2 < groups) issue(k + 2, slotNext);
+        if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
+        mbarWait(ringBar + 8u * slot, (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+        const uint32_t slotAddr = ringAddr + slot * kGroupBytes;
+        if (KIND != kKindBytes) In::storeGroup(slotAddr, planes, elem0 + k * (U * 32), lane);
+        encodeGroup<WIDE, KIND>(state, slotAddr + lane * WB, rc, wa);
+        slot = slot + 1 == In::kRingSlots ? 0u : slot + 1;
+        slotNext = slotNext + 1 == In::kRingSlots ? 0u : slotNext + 1;
+      }
+      *ringPhase = phases;
+    } else {
+      // input rows stream through the cp.async ring, two groups ahead of the encoder
+      const uint8_t* src = in + lane * 16u;
+      const uint32_t dst = ringAddr + lane * 16u;
+      auto issue = [&](uint32_t g, uint32_t slot) {
 #pragma unroll
-      for (uint32_t c = 0; c < kChunks; ++c)
-        cpAsync16(dst + slot * kGroupBytes + c * 512u, src + (size_t)g * kGroupBytes + c * 512u);
-    };
-    if (groups > 0) issue(0, 0);
-    cpAsyncCommit();
-    if (groups > 1) issue(1, 1);
-    cpAsyncCommit();
-    uint32_t slot = 0, slotNext = 2 % In::kRingSlots;
-    for (uint32_t k = 0; k < groups; ++k) {
-      if (k + 2 < groups) issue(k + 2, slotNext);
+        for (uint32_t c = 0; c < kChunks; ++c)
+          cpAsync16(dst + slot * kGroupBytes + c * 512u, src + (size_t)g * kGroupBytes + c * 512u);
+      };
+      if (groups > 0) issue(0, 0);
       cpAsyncCommit();
-      if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
-      cpAsyncWait<2>();
-      __syncwarp();
-      const uint32_t slotAddr = ringAddr + slot * kGroupBytes;
-      if (KIND != kKindBytes) In::storeGroup(slotAddr, planes, elem0 + k * (U * 32), lane);
-      encodeGroup<WIDE, KIND>(state, slotAddr + lane * WB, rc, wa);
-      slot = slot + 1 == In::kRingSlots ? 0u : slot + 1;
-      slotNext = slotNext + 1 == In::kRingSlots ? 0u : slotNext + 1;
+      if (groups > 1) issue(1, 1);
+      cpAsyncCommit();
+      uint32_t slot = 0, slotNext = 2 % In::kRingSlots;
+      for (uint32_t k = 0; k < groups; ++k) {
+        if (k + 2 < groups) issue(k + 2, slotNext);
+        cpAsyncCommit();
+        if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
+        cpAsyncWait<2>();
+        __syncwarp();
+        const uint32_t slotAddr = ringAddr + slot * kGroupBytes;
+        if (KIND != kKindBytes) In::storeGroup(slotAddr, planes, elem0 + k * (U * 32), lane);
+        encodeGroup<WIDE, KIND>(state, slotAddr + lane * WB, rc, wa);
+        slot = slot + 1 == In::kRingSlots ? 0u : slot + 1;
+        slotNext = slotNext + 1 == In::kRingSlots ? 0u : slotNext + 1;
+      }
     }
     r = groups * U;
   }
@@ -1079,8 +1051,8 @@ __global__ void encodeKernel(EncodeScratch sc, int pb, bool useChecksum,
     const uint32_t blockLen = min(kBlockBytes, size - start);
     uint32_t state;
     Spill sp{nullptr, 0u, 0u};  // worst-case sized slot: never spills
-    const uint32_t words = encodeBlockWarp<false, KIND>(ansIn + (size_t)start * EncIn<KIND>::kWordBytes, blockLen, start, planes,
-                                                        tabAddr, pb, stageAddr, myStage, sp, ringAddr, lane, state);
+    const uint32_t words = encodeBlockWarp<false, KIND, false>(ansIn + (size_t)start * EncIn<KIND>::kWordBytes, blockLen, start, planes,
+                                                               tabAddr, pb, stageAddr, myStage, sp, ringAddr, lane, state);
     const uint32_t padded = roundUp(words, 8u);
 
     // ---- packed offset of this block: look-back over the member's earlier tickets ----
@@ -1136,13 +1108,24 @@ __host__ __device__ constexpr uint32_t encFastWarpSmem(uint32_t slotWords, int k
 }
 
 // Per-warp view of the CTA's dynamic shared memory: [input ring | staging slot] per warp.
+#ifndef DGB_ENC_TMA
+#define DGB_ENC_TMA 0
+#endif
+// input rows by per-lane cp.async (0, default) or by TMA bulk copy (1).  A/B on B200, encode call, cp.async / TMA:
+// c3 185.7 / 192.1 us, c4 209.5 / 212.0, c2 358.0 / 363.3 (profiles/r02_ab_tma_input_ring.txt): one lane issuing the bulk
+// copy and 32 lanes polling the mbarrier cost more than the two LDGSTS per lane they replace.
+constexpr bool kEncTma = DGB_ENC_TMA != 0;
+
 struct WarpSmem {
   uint32_t ringAddr, stageAddr;
   uint16_t* stage;
   Spill sp;
+  uint32_t ringBar;    // shared address of this warp's ring mbarriers (one per slot)
+  uint32_t ringPhase;  // bit s = parity the next wait on slot s expects
 };
 __device__ __forceinline__ WarpSmem warpSmem(const EncodeScratch& sc, uint8_t* smem, uint32_t warp, uint32_t W,
-                                             uint32_t slotWords, int pb, int kind, uint32_t spillWarpBase) {
+                                             uint32_t slotWords, int pb, int kind, uint32_t spillWarpBase,
+                                             unsigned long long (*ringBars)[4]) {
   WarpSmem ws;
   uint8_t* mine = smem + (size_t)warp * encFastWarpSmem(slotWords, kind);
   ws.ringAddr = smemAddr(mine);
@@ -1153,6 +1136,11 @@ __device__ __forceinline__ WarpSmem warpSmem(const EncodeScratch& sc, uint8_t* s
   ws.sp.spilled = 0;
   ws.stage = reinterpret_cast<uint16_t*>(mine + encRingBytes(kind));
   ws.stageAddr = smemAddr(ws.stage);
+  ws.ringBar = smemAddr(&ringBars[warp][0]);  // static shared memory: the dynamic region is reused by statistics items
+  ws.ringPhase = 0;
+  if (kEncTma && (threadIdx.x & 31u) == 0) {
+    for (uint32_t k = 0; k < 4; ++k) mbarInit(ws.ringBar + 8u * k, 1);
+  }
   return ws;
 }
 
@@ -1200,8 +1188,9 @@ __device__ __forceinline__ void encodeMemberBlocks(const EncodeScratch& sc, cons
     const uint32_t start = block * kBlockBytes;
     const uint32_t blockLen = min(kBlockBytes, size - start);
     uint32_t state;
-    const uint32_t words = encodeBlockWarp<WIDE, KIND>(ansIn + (size_t)start * EncIn<KIND>::kWordBytes, blockLen, start, planes,
-                                                       tabAddr, pb, ws.stageAddr, ws.stage, ws.sp, ws.ringAddr, lane, state);
+    const uint32_t words = encodeBlockWarp<WIDE, KIND, kEncTma>(ansIn + (size_t)start * EncIn<KIND>::kWordBytes, blockLen, start,
+                                                                planes, tabAddr, pb, ws.stageAddr, ws.stage, ws.sp, ws.ringAddr,
+                                                                lane, state, ws.ringBar, &ws.ringPhase);
     const uint32_t padded = roundUp(words, 8u);
     // take a place in the data section: one 64-bit atomic hands out the word offset (low half)
     // and counts finished blocks (high half), so no fence is needed to order the two
@@ -1240,7 +1229,12 @@ encodeKernelFast(EncodeScratch sc, int pb, bool useChecksum,
   const uint32_t t = threadIdx.x, lane = t & 31u;
   const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
   const uint32_t W = blockDim.x >> 5;
-  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, KIND, spillWarpBase);
+  __shared__ __align__(8) unsigned long long sRingBar[8][4];
+  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, KIND, spillWarpBase, sRingBar);
+  if (kEncTma) {
+    fenceBarrierInit();
+    __syncthreads();
+  }
   const uint32_t tabAddr = smemAddr(sTab);
 
   const uint64_t g = gridDim.x, span = blockEnd - blockBegin;
@@ -1327,7 +1321,12 @@ encodeFusedKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven,
     fenceBarrierInit();
     __syncthreads();
   }
-  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, KIND, 0u);
+  __shared__ __align__(8) unsigned long long sRingBar[8][4];
+  WarpSmem ws = warpSmem(sc, smem, warp, W, slotWords, pb, KIND, 0u, sRingBar);
+  if (kEncTma) {
+    fenceBarrierInit();
+    __syncthreads();
+  }
   const uint32_t tabAddr = smemAddr(sTab);
   const bool preferStats = statsEvery != 0u && (blockIdx.x % statsEvery) == 0u;
 
