@@ -615,17 +615,11 @@ def main():
     roofline = None
     roofline_all = {}
     if "kernels" in main_res:
-        # compulsory bytes per launch given the two-kernel split of each direction:
-        #   floats: stats  reads 2F(words) writes the stored plane(s) + header, decode reads C_f writes 2F
-        #   encode reads the F comp bytes and writes the ANS archive
-        nfl = ubytes // (2 if kind in ("bf16", "f16") else 1)
-        # the fused encoder is ONE launch per call: its algorithmic bytes are the whole direction's, U + C
-        if kind == "bytes":
-            alg = {"stats": ubytes, "encode": ubytes + cbytes, "decode": cbytes + ubytes, "encode_fused": ubytes + cbytes}
-        else:
-            ans_bytes = cbytes - (nfl + 16 * main_res["batch"])
-            alg = {"stats": ubytes + nfl, "encode": nfl + ans_bytes, "decode": cbytes + ubytes,
-                   "encode_fused": ubytes + cbytes}
+        # compulsory bytes per launch: the statistics kernel is a pure read of the raw
+        # input (U); the coder reads the raw input again and writes the whole archive (U + C: stored planes + ANS
+        # part for float kinds); the decoder reads the archive and writes the output (C + U).  The single-launch
+        # (fused) encoder does the statistics read and the coder's work in one launch (counted U + C).
+        alg = {"stats": ubytes, "encode": ubytes + cbytes, "decode": cbytes + ubytes, "encode_fused": ubytes + cbytes}
         for k, v in main_res["kernels"].items():
             if k in alg:
                 a = alg[k] / (v["ms_avg"] / 1e3) / 1e9

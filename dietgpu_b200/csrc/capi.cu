@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,9 +26,13 @@ namespace {
 struct TimedLaunch { int slot; cudaEvent_t a, b; };
 std::vector<TimedLaunch>& timedLaunches() { static std::vector<TimedLaunch> v; return v; }
 std::vector<cudaEvent_t>& eventPool() { static std::vector<cudaEvent_t> v; return v; }
+std::mutex& timerMutex() { static std::mutex m; return m; }  // guards the two vectors above (calls may come from several host threads)
 cudaEvent_t takeEvent() {
-  auto& pool = eventPool();
-  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  {
+    std::lock_guard<std::mutex> lock(timerMutex());
+    auto& pool = eventPool();
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  }
   cudaEvent_t e = nullptr;
   cudaEventCreate(&e);
   return e;
@@ -49,11 +54,23 @@ int streamPool(StreamPool** out) {
   if (dev < 0 || dev >= kMaxDevices) return DGB_ERR_INVALID_ARG;
   Slot& sl = slots[dev];
   if (!sl.ready) {
-    for (int i = 0; i < kMaxParts; ++i) {
-      DGB_CUDA_TRY(cudaStreamCreateWithFlags(&sl.pool.s[i], cudaStreamNonBlocking));
-      DGB_CUDA_TRY(cudaEventCreateWithFlags(&sl.pool.done[i], cudaEventDisableTiming));
+    // all or nothing: a partly created pool is torn down again, so a later call can retry cleanly
+    StreamPool p{};
+    bool ok = cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < kMaxParts; ++i) {
+      ok = cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming) == cudaSuccess;
     }
-    DGB_CUDA_TRY(cudaEventCreateWithFlags(&sl.pool.start, cudaEventDisableTiming));
+    if (!ok) {
+      setLastCudaError(cudaGetLastError());
+      if (p.start) cudaEventDestroy(p.start);
+      for (int i = 0; i < kMaxParts; ++i) {
+        if (p.s[i]) cudaStreamDestroy(p.s[i]);
+        if (p.done[i]) cudaEventDestroy(p.done[i]);
+      }
+      return DGB_ERR_CUDA;
+    }
+    sl.pool = p;
     sl.ready = true;
   }
   *out = &sl.pool;
@@ -104,6 +121,7 @@ void timerBegin(int slot, cudaStream_t stream) {
 void timerEnd(int slot, cudaStream_t stream) {
   if (!options().timing) return;
   cudaEventRecord(tlsOpen[slot].b, stream);
+  std::lock_guard<std::mutex> lock(timerMutex());
   timedLaunches().push_back(tlsOpen[slot]);
 }
 
@@ -360,6 +378,7 @@ static int* optionSlot(const char* name) {
   Options& o = options();
   if (!name) return nullptr;
   if (!std::strcmp(name, "decode_fused")) return &o.decode_fused;
+  if (!std::strcmp(name, "decode_warps")) return &o.decode_warps;
   if (!std::strcmp(name, "decode_slot_words")) return &o.decode_slot_words;
   if (!std::strcmp(name, "encode_warps")) return &o.encode_warps;
   if (!std::strcmp(name, "encode_canonical")) return &o.encode_canonical;
@@ -369,6 +388,9 @@ static int* optionSlot(const char* name) {
   if (!std::strcmp(name, "fused_chunk_blocks")) return &o.fused_chunk_blocks;
   if (!std::strcmp(name, "encode_wide_table")) return &o.encode_wide_table;
   if (!std::strcmp(name, "encode_slot_words")) return &o.encode_slot_words;
+  if (!std::strcmp(name, "stats_stage")) return &o.stats_stage;
+  if (!std::strcmp(name, "stats_stage_kb")) return &o.stats_stage_kb;
+  if (!std::strcmp(name, "encode_k2_ctas")) return &o.encode_k2_ctas;
   if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
   if (!std::strcmp(name, "hist_ctas_per_sm")) return &o.hist_ctas_per_sm;
   if (!std::strcmp(name, "timing")) return &o.timing;
@@ -387,6 +409,7 @@ int dgb_set_option(const char* name, int value) {
 // call; synchronises the device.  Slots: 0 stats(K1) 1 encode(K2) 2 plan 3 decode 4 checksum.
 int dgb_kernel_times(float* ms, int* counts, int nslots) {
   if (cudaDeviceSynchronize() != cudaSuccess) return DGB_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(timerMutex());
   for (int i = 0; i < nslots; ++i) { if (ms) ms[i] = 0.f; if (counts) counts[i] = 0; }
   for (auto& t : timedLaunches()) {
     float e = 0.f;

@@ -72,6 +72,7 @@ struct __align__(16) EncEntryWide {
 // ---- tuning options (dgb_set_option) ---------------------------------------
 struct Options {
   int decode_fused = 1;      // 1: one persistent launch, CTAs lease members and warps claim blocks; 0: plan + decode kernels
+  int decode_warps = 8;      // single-launch decoder: warps per CTA (4 or 8)
   int decode_slot_words = 0; // TMA staging slot per warp in u16 words; 0 = auto
   int encode_warps = 8;      // warps per encode CTA (each warp is an independent worker)
   int encode_slot_words = 0; // staging slot of the fast encoder in u16 words; 0 = auto
@@ -81,6 +82,9 @@ struct Options {
   int fused_stats_every = 4; // fused launch: one CTA in this many prefers statistics items (0: none does)
   int fused_chunk_blocks = 16;  // fused launch: 4 KiB blocks per encode chunk
   int encode_wide_table = -1;  // encoder table entries: 1 = 16 B, 0 = 8 B, -1 = by data kind (bf16/fp32 wide)
+  int stats_stage = 0;       // two-kernel path, float kinds: 1 = statistics slab lands in shared memory by TMA (one slab per CTA)
+  int stats_stage_kb = 32;   // ... slab size for that
+  int encode_k2_ctas = 0;    // cap of coder CTAs per SM (0 = as many as fit)
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_ctas_per_sm = 32; // stats grid = this many CTAs per SM (each CTA loops over slabs)
   int parts = 0;             // sub-batches run on internal streams (0 = auto, 1 = off, max 4)

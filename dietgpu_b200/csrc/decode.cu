@@ -348,7 +348,11 @@ __device__ __forceinline__ void refill(uint32_t& state, Stream& st, uint32_t geM
   if (rd) state = (state << 16) + st.pop(__popc(vote & geMask));
   st.retreat(__popc(vote));
 }
-// shared-memory flavour in PTX: one predicate feeds the vote, the load and the state update
+// shared-memory flavour in PTX: one predicate feeds the vote and the state update.  The load itself is NOT
+// predicated: a predicated load leaves its destination "maybe written", which ptxas turns into one
+// loop-carried register per unrolled row (16 registers of dead values in the round-1 kernel, spills in the
+// free-running one).  Lanes that do not refill read at most 64 B below the stream, i.e. inside the slot's
+// lane-state area, and drop the value.
 template <>
 __device__ __forceinline__ void refill<SmemStream>(uint32_t& state, SmemStream& st, uint32_t geMask) {
   asm volatile(
@@ -361,7 +365,7 @@ __device__ __forceinline__ void refill<SmemStream>(uint32_t& state, SmemStream& 
       "popc.b32 t, t;\n"
       "shl.b32 t, t, 1;\n"
       "sub.u32 a, %1, t;\n"
-      "@p ld.shared.u16 w, [a];\n"
+      "ld.shared.u16 w, [a];\n"  // unpredicated on purpose (see below)
       "@p mad.lo.u32 %0, %0, 65536, w;\n"
       "popc.b32 t, v;\n"
       "shl.b32 t, t, 1;\n"
@@ -601,6 +605,11 @@ decodeKernel(DecodeScratch sc, uint32_t m0, uint32_t m1, uint32_t part, uint32_t
 // of the two-kernel path left SMs idle for ~15 % of the kernel, ncu r01).  The first CTA to lease a
 // member reports outSuccess / outSize (ans/GpuANSDecode.cuh:326-341 semantics); claims past the
 // archive's real block count, or of a member that failed, are dropped.
+// Measured and rejected (profiles/r02_wall_experiments.txt, step L): a variant without the lease-end
+// barrier -- two LUT buffers per CTA, a generation counter, the first warp to run dry builds the next
+// LUT alone while the others keep decoding -- was slower on every workload (c3 151.8 vs 143.7 us,
+// c2 319 vs 245): a member runs dry for all of its warps within one block time, so they all arrive
+// together anyway and then wait for a single-warp LUT build instead of sharing it.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kNoMember = 0xffffffffu;
 
@@ -848,11 +857,10 @@ int launchDecodeW(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t pa
   return launchDecode<KIND, PB, 8, true, false>(sc, m0, m1, part, blockBound, stream);
 }
 
-template <int KIND, int PB>
-int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
-                      uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
-                      cudaStream_t stream) {
-  constexpr int WARPS = 8;
+template <int KIND, int PB, int WARPS>
+int launchDecodeFusedW(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
+                       uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
+                       cudaStream_t stream) {
   auto kern = decodeFusedKernel<KIND, PB, WARPS>;
   // staging slot per warp: worst case for raw bytes; float kinds code exponent-like bytes that
   // compress well, so a smaller slot (more resident warps) covers them and rare larger blocks
@@ -881,6 +889,16 @@ int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
   DGB_CUDA_TRY(cudaGetLastError());
   timerEnd(kSlotDecode, stream);
   return DGB_OK;
+}
+
+template <int KIND, int PB>
+int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
+                      uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
+                      cudaStream_t stream) {
+  // warps per CTA = warps that share one LUT and meet at the barrier when a lease ends
+  if (options().decode_warps == 4)
+    return launchDecodeFusedW<KIND, PB, 4>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+  return launchDecodeFusedW<KIND, PB, 8>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
 }
 
 template <int KIND>

@@ -474,6 +474,29 @@ statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, 
   statsFloatItem<FT, false>(sc, sHist, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y, gridDim.y, outSize);
 }
 
+// K1 with the slab landed in shared memory by one TMA bulk copy per CTA (option stats_stage): the
+// bytes in flight per SM no longer depend on the number of resident statistics warps, so the kernel
+// keeps its bandwidth when it only gets the SM resources the coder of the previous sub-batch leaves
+// free.  gridDim.y must equal the slab count (one slab per CTA); dynamic shared memory = slab bytes.
+template <int FT>
+__global__ void __launch_bounds__(kStatsThreads)
+statsFloatStagedKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, uint32_t memberBase,
+                       uint32_t* __restrict__ outSize) {
+  extern __shared__ __align__(16) uint8_t stageSmem[];
+  __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
+  __shared__ __align__(8) unsigned long long sBar;
+  uint32_t phase = 0;
+  StatsStage stage;
+  stage.buf = reinterpret_cast<uint4*>(stageSmem);
+  stage.bar = smemAddr(&sBar);
+  stage.phase = &phase;
+  if (threadIdx.x == 0) mbarInit(stage.bar, 1);
+  fenceBarrierInit();
+  __syncthreads();
+  statsFloatItem<FT, true>(sc, sHist, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y, gridDim.y, outSize,
+                           stage);
+}
+
 // ---------------------------------------------------------------------------
 // K2: the rANS state machine + single-pass packing.
 //
@@ -555,6 +578,11 @@ struct EncIn16 {
   template <int J, uint32_t STRIDE>
   static __device__ __forceinline__ uint32_t tabOffset(uint32_t ringLane) {
     uint32_t w;
+    if (KIND == kKindF16) {
+      // the coded byte of fp16 IS the word's high byte: read it alone, no shift / mask
+      asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(w) : "r"(ringLane), "n"(J * 64 + 1));
+      return STRIDE * w;
+    }
     asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(w) : "r"(ringLane), "n"(J * 64));
     return tabOffsetOf<STRIDE>(w);
   }
@@ -1712,7 +1740,12 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     const int rc = DGB_BY_KIND(kind, residentPerSm(variant, W, smemBytes, &perSm));
     if (rc != DGB_OK) return rc;
   }
+  // option encode_k2_ctas caps the coder's CTAs per SM so that the statistics kernel of the next
+  // sub-batch finds room beside it (0 = as many as fit)
+  if (opt.encode_k2_ctas > 0) perSm = std::min(perSm, opt.encode_k2_ctas);
   const uint64_t resident = (uint64_t)perSm * sms;
+  int devForAttr = 0;
+  DGB_CUDA_TRY(cudaGetDevice(&devForAttr));
   const uint32_t spillWarpsPerPart = sp.spillWarps / (uint32_t)parts;
 
   for (int part = 0; part < parts; ++part) {
@@ -1728,13 +1761,34 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
     uint32_t partMax = 0;
     for (uint32_t i = m0; i < m1; ++i) partMax = std::max(partMax, desc[i].size);
     const uint64_t maxVecs = ((uint64_t)partMax * elemBytes) / 16u;
-    uint32_t gridY = (uint32_t)std::max<uint64_t>(1, (maxVecs + slabVecs - 1) / slabVecs);
-    // enough CTAs to fill the machine a few times, never more than the slabs
-    const uint32_t wantY = std::max(1u, (uint32_t)(std::max(1, opt.hist_ctas_per_sm) * sms) / (m1 - m0));
-    gridY = std::min(std::min(gridY, wantY), 65535u);
+    const bool stagedK1 = kind != kKindBytes && opt.stats_stage != 0;
+    const uint32_t slabVecsK1 = stagedK1 ? std::min<uint32_t>(slabVecs, (uint32_t)std::max(1, opt.stats_stage_kb) * 64u) : slabVecs;
+    uint32_t gridY = (uint32_t)std::max<uint64_t>(1, (maxVecs + slabVecsK1 - 1) / slabVecsK1);
+    if (!stagedK1) {
+      // enough CTAs to fill the machine a few times, never more than the slabs
+      const uint32_t wantY = std::max(1u, (uint32_t)(std::max(1, opt.hist_ctas_per_sm) * sms) / (m1 - m0));
+      gridY = std::min(gridY, wantY);
+    }
+    gridY = std::min(gridY, 65535u);
     dim3 grid1(m1 - m0, gridY);
     timerBegin(kSlotStats, ps);
-    if (kind == kKindBytes) {
+    if (stagedK1 && gridY * (uint64_t)slabVecsK1 >= maxVecs) {
+      const size_t stageBytes = (size_t)slabVecsK1 * 16u;
+      static thread_local int stagedDev = -1;
+      if (stagedDev != devForAttr) {
+        DGB_CUDA_TRY(cudaFuncSetAttribute(statsFloatStagedKernel<DGB_FLOAT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        DGB_CUDA_TRY(cudaFuncSetAttribute(statsFloatStagedKernel<DGB_BFLOAT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        DGB_CUDA_TRY(cudaFuncSetAttribute(statsFloatStagedKernel<DGB_FLOAT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        stagedDev = devForAttr;
+      }
+      if (kind == kKindF16) {
+        statsFloatStagedKernel<DGB_FLOAT16><<<grid1, kStatsThreads, stageBytes, ps>>>(sc, pb, checksum, slabVecsK1, m0, outSize_dev);
+      } else if (kind == kKindBF16) {
+        statsFloatStagedKernel<DGB_BFLOAT16><<<grid1, kStatsThreads, stageBytes, ps>>>(sc, pb, checksum, slabVecsK1, m0, outSize_dev);
+      } else {
+        statsFloatStagedKernel<DGB_FLOAT32><<<grid1, kStatsThreads, stageBytes, ps>>>(sc, pb, checksum, slabVecsK1, m0, outSize_dev);
+      }
+    } else if (kind == kKindBytes) {
       statsBytesKernel<<<grid1, kStatsThreads, 0, ps>>>(sc, histogram_dev, pb, checksum, slabVecs, m0, outSize_dev);
     } else if (kind == kKindF16) {
       statsFloatKernel<DGB_FLOAT16><<<grid1, kStatsThreads, 0, ps>>>(sc, pb, checksum, slabVecs, m0, outSize_dev);

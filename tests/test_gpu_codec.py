@@ -473,6 +473,7 @@ def test_kernel_variants_agree():
         dict(encode_fused=0, decode_fused=0),
         dict(encode_fused=1, decode_fused=0),
         dict(encode_fused=0, decode_fused=1),
+        dict(encode_fused=1, fused_chunk_blocks=2),
         dict(fused_chunk_blocks=1),
         dict(fused_chunk_blocks=3, fused_stage=0),
         dict(fused_chunk_blocks=64),
