@@ -16,9 +16,19 @@ caller's device; there is no CPU fallback for it.  The exchange itself is torch.
 NCCL moves device buffers directly; on a backend without device collectives (gloo, used by the
 single-GPU multi-process tests) the packed archives are staged through host memory.
 
-Break-even (profiles/r01_allgather_2gpu.txt): on NVLink 5 (900 GB/s) a plain all-gather of 64 MiB per
-rank takes 0.21 ms and the compressed one 0.77 ms, so this only pays on links slower than ~100 GB/s
-(inter-node), which is where the reference aims it.
+Two transports:
+
+  * NCCL (default; any backend torch.distributed offers, gloo for the single-GPU tests): archives are
+    packed and exchanged by collectives.  Break-even (profiles/r01_allgather_2gpu.txt): on NVLink 5 a plain
+    all-gather of 64 MiB per rank takes 0.21 ms and this one 0.77 ms, so it pays on links slower than
+    ~100 GB/s (inter-node), which is where the reference aims it.
+  * peer memory (`PeerWorkspace`, one node, NVLink / NVSwitch): every rank encodes into a buffer its peers
+    have mapped (torch symmetric memory: CUDA VMM handles exchanged once at set-up), one device-side
+    barrier, and then the DECODE KERNEL ITSELF reads the peers' archives over NVLink -- its TMA bulk
+    copies and cp.async rings take peer addresses like local ones, so the transfer is the decoder's own
+    input traffic, block by block, and needs no copy kernel, no packing, no size exchange (the decoder
+    reads sizes from the archive headers) and no host synchronisation.  A rank encodes ONCE and every
+    peer pulls, so the codec cost is amortised over world - 1 links (profiles/r02_allgather_p2p.txt).
 """
 from __future__ import annotations
 
@@ -111,6 +121,82 @@ def exchange_archives(rows: Sequence[torch.Tensor], group=None) -> List[List[tor
     return _Exchange(rows, group).wait()
 
 
+class PeerWorkspace:
+    """A byte buffer of `nbytes` per rank that every rank of `group` (one node) has mapped into its own address
+    space.  Setting it up is a collective (allocation + handle exchange); keep it and pass it to every
+    `*_compressed(..., peer=ws)` call.  The buffer is used in two halves, alternating per call: the
+    barrier of call k+1 orders every rank's reads of call k before any rank's writes of call k+2, so
+    one device-side barrier per collective is enough."""
+
+    def __init__(self, nbytes: int, group=None, device: Optional[torch.device] = None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        if dist.get_backend(self.group) != "nccl":
+            raise RuntimeError("PeerWorkspace: peer-mapped memory needs one CUDA device per rank (NCCL group)")
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.half = _round_up(int(nbytes), 256)
+        self.buf = symm.empty(2 * self.half, dtype=torch.uint8, device=dev)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.calls = 0
+        self._views = {}
+
+    def begin(self, nbytes: int) -> int:
+        """Byte offset of the half this call uses."""
+        if nbytes > self.half:
+            raise ValueError(f"PeerWorkspace: call needs {nbytes} B per rank, workspace halves hold {self.half} B")
+        off = (self.calls & 1) * self.half
+        self.calls += 1
+        return off
+
+    def view(self, rank: int, offset: int, nbytes: int) -> torch.Tensor:
+        """uint8 tensor on THIS rank's device that aliases bytes [offset, offset + nbytes) of `rank`'s buffer."""
+        if rank == self.rank:
+            return self.buf[offset:offset + nbytes]
+        key = (rank, offset, nbytes)
+        v = self._views.get(key)
+        if v is None:
+            v = self._views[key] = self.hdl.get_buffer(rank, (nbytes,), torch.uint8, offset)
+        return v
+
+    def barrier(self) -> None:
+        """Device-side barrier of all ranks on the current stream (no host synchronisation)."""
+        self.hdl.barrier(channel=0)
+
+
+def _archive_cols(as_float: bool, dtype: torch.dtype, longest: int) -> int:
+    """Row pitch for archives of members of at most `longest` elements (bytes for the byte codec)."""
+    b = ops.max_float_compressed_size(torch.empty(0, dtype=dtype), longest) if as_float else ops.max_any_compressed_size(longest)
+    return _round_up(int(b), _ALIGN)
+
+
+def _all_gather_peer(flat: torch.Tensor, as_float: bool, bounds: List[int], ws: PeerWorkspace, checksum: bool,
+                     temp_mem: Optional[torch.Tensor], check: bool) -> torch.Tensor:
+    n, members, world, rank = flat.numel(), len(bounds) - 1, ws.world, ws.rank
+    cols = _archive_cols(as_float, flat.dtype, max(bounds[i + 1] - bounds[i] for i in range(members)))
+    off = ws.begin(members * cols)
+    out = torch.empty(world * n, dtype=flat.dtype, device=flat.device)
+    mine = ws.view(rank, off, members * cols).view(members, cols)
+    sizes = torch.empty(members, dtype=torch.int32, device=flat.device)
+    ops.compress_data(as_float, [flat[bounds[i]:bounds[i + 1]] for i in range(members)], checksum, temp_mem, mine, sizes)
+    ws.barrier()  # every rank's archives are complete (and every rank is done with the previous call's other half)
+    out[rank * n:(rank + 1) * n].copy_(flat)  # own shard: a local copy, no codec
+    ins, outs = [], []
+    for k in range(1, world):
+        w = (rank + k) % world  # start with a different peer on every rank: spreads the pulls over the links
+        rows = ws.view(w, off, members * cols).view(members, cols)
+        for i in range(members):
+            ins.append(rows[i])
+            outs.append(out[w * n + bounds[i]: w * n + bounds[i + 1]])
+    if ins:
+        status = torch.zeros(len(ins), dtype=torch.uint8, device=flat.device)
+        ops.decompress_data(as_float, ins, outs, checksum, temp_mem, status)
+        if check and not bool(status.all()):
+            raise RuntimeError("all_gather_compressed: a peer archive failed to decode")
+    return out
+
+
 def _split(n: int, parts: int, quantum: int) -> List[int]:
     """Boundaries of `parts` nearly equal pieces of [0, n), interior boundaries multiples of `quantum`."""
     parts = max(1, min(parts, max(1, n // max(quantum, 1))))
@@ -119,11 +205,15 @@ def _split(n: int, parts: int, quantum: int) -> List[int]:
 
 
 def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksum: bool = False,
-                          temp_mem: Optional[torch.Tensor] = None, stages: int = 2) -> torch.Tensor:
+                          temp_mem: Optional[torch.Tensor] = None, stages: int = 2,
+                          peer: Optional[PeerWorkspace] = None, check: bool = True) -> torch.Tensor:
     """Every rank contributes the CUDA tensor `t` (same shape and dtype on every rank; fp16 / bf16 / fp32 go
     through the float codec, anything else through the byte codec) and receives the concatenation
     [world * t.numel()] in rank order, bit-exact.  `members` = archives per rank (the codec's parallelism
-    comes from blocks, so a handful is enough); `stages` = pipeline pieces (see the module docstring)."""
+    comes from blocks, so a handful is enough); `stages` = pipeline pieces (see the module docstring).
+    With `peer` (a PeerWorkspace of the same group) the archives are pulled over NVLink by the decode kernel
+    instead of being exchanged by a collective; `check=False` then skips the only host synchronisation (the
+    read of the decode status)."""
     if not t.is_cuda or not t.is_contiguous():
         raise ValueError("all_gather_compressed: contiguous CUDA tensor expected (no CPU fallback)")
     as_float = t.dtype in (torch.float16, torch.bfloat16, torch.float32)
@@ -133,6 +223,9 @@ def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksu
     # equal member lengths (multiples of 8 elements keep every member 16 B aligned); the last takes the rest
     bounds = _split(n, members, 8)
     members = len(bounds) - 1
+    if peer is not None:
+        out = _all_gather_peer(flat, as_float, bounds, peer, checksum, temp_mem, check)
+        return out if as_float else out.view(t.dtype)
     world = _world(group)
     out = torch.empty(world * n, dtype=flat.dtype, device=t.device)
     stages = max(1, min(int(stages), members))
@@ -174,8 +267,36 @@ def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksu
     return out if as_float else out.view(t.dtype)
 
 
+def _all_to_all_peer(flats: List[torch.Tensor], as_float: bool, ws: PeerWorkspace, checksum: bool,
+                     temp_mem: Optional[torch.Tensor], check: bool) -> List[torch.Tensor]:
+    """Regular all-to-all (chunk (s, d) has the same length on every rank pair): rank r encodes its chunks as one
+    batch into its own peer-mapped rows, and after the barrier decodes row [r] of every peer straight out of
+    the peer's memory."""
+    world, rank, dev = ws.world, ws.rank, flats[0].device
+    m = flats[0].numel()
+    if any(f.numel() != m for f in flats):
+        raise ValueError("all_to_all_compressed(peer=...): equal chunk lengths expected (sizes are not exchanged)")
+    cols = _archive_cols(as_float, flats[0].dtype, m)
+    off = ws.begin(world * cols)
+    mine = ws.view(rank, off, world * cols).view(world, cols)
+    sizes = torch.empty(world, dtype=torch.int32, device=dev)
+    ops.compress_data(as_float, flats, checksum, temp_mem, mine, sizes)
+    ws.barrier()
+    outs = [torch.empty(m, dtype=flats[0].dtype, device=dev) for _ in range(world)]
+    outs[rank].copy_(flats[rank])
+    order = [(rank + k) % world for k in range(1, world)]
+    ins = [ws.view(s, off + rank * cols, cols) for s in order]
+    if order:
+        status = torch.zeros(len(order), dtype=torch.uint8, device=dev)
+        ops.decompress_data(as_float, ins, [outs[s] for s in order], checksum, temp_mem, status)
+        if check and not bool(status.all()):
+            raise RuntimeError("all_to_all_compressed: a peer archive failed to decode")
+    return outs
+
+
 def all_to_all_compressed(chunks: Sequence[torch.Tensor], group=None, checksum: bool = False,
-                          temp_mem: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+                          temp_mem: Optional[torch.Tensor] = None, peer: Optional[PeerWorkspace] = None,
+                          check: bool = True) -> List[torch.Tensor]:
     """chunks[d] (CUDA, contiguous, same dtype and shape on every rank for a given (source, destination) pair is
     NOT required: sizes travel with the data) goes to rank d; returns [world] tensors, entry s = what rank s
     sent here, bit-exact.  One archive per destination; the payload moves with all_to_all_single and exact
@@ -189,6 +310,9 @@ def all_to_all_compressed(chunks: Sequence[torch.Tensor], group=None, checksum: 
             raise ValueError("all_to_all_compressed: contiguous CUDA tensors of one dtype on one device expected")
     as_float = dt in (torch.float16, torch.bfloat16, torch.float32)
     flats = [c.reshape(-1) if as_float else c.reshape(-1).view(torch.uint8) for c in chunks]
+    if peer is not None:
+        outs = _all_to_all_peer(flats, as_float, peer, checksum, temp_mem, check)
+        return [x if as_float else x.view(dt) for x in outs]
     comp, sizes, _ = ops.compress_data(as_float, flats, checksum, temp_mem)
     if world == 1:
         out = torch.empty_like(flats[0])

@@ -393,6 +393,7 @@ static int* optionSlot(const char* name) {
   if (!std::strcmp(name, "encode_k2_ctas")) return &o.encode_k2_ctas;
   if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
   if (!std::strcmp(name, "hist_ctas_per_sm")) return &o.hist_ctas_per_sm;
+  if (!std::strcmp(name, "inline_members")) return &o.inline_members;
   if (!std::strcmp(name, "timing")) return &o.timing;
   if (!std::strcmp(name, "parts")) return &o.parts;
   return nullptr;

@@ -53,6 +53,24 @@ struct MemberDesc {
 };
 static_assert(sizeof(MemberDesc) == 24, "");
 
+// Batches of up to kInlineMembers members travel to the default kernels INSIDE the kernel parameters
+// (constant bank, 1.5 KB) instead of through a host-to-device copy in front of the first launch: one
+// dependent DMA less per call, nothing of the caller's host memory is read after the call returns,
+// and the whole call can be captured into a CUDA graph.  Larger batches (and the optional kernel
+// flavours) read the same table from the scratch buffer.
+constexpr uint32_t kInlineMembers = 64;
+struct InlineMembers {
+  uint32_t count;  // 0: the table is in global memory (scratch)
+  uint32_t pad;
+  MemberDesc m[kInlineMembers];
+};
+__device__ __forceinline__ MemberDesc memberAt(const InlineMembers& im, const MemberDesc* global, uint32_t i) {
+  return im.count ? im.m[i] : global[i];
+}
+__device__ __forceinline__ uint32_t memberWork0(const InlineMembers& im, const MemberDesc* global, uint32_t i) {
+  return im.count ? im.m[i].work0 : __ldg(&global[i].work0);
+}
+
 // ---- encoder symbol table entry (one per symbol, 8 B, shared memory) -------
 // magic = ceil(2^(32+shift)/pdf): state / pdf == hi32(state * magic) >> shift for state < 2^31
 //         (the quotient ans/GpuANSStatistics.cuh:343-358 computes, without its add; pdf == 1 uses
@@ -88,6 +106,7 @@ struct Options {
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_ctas_per_sm = 32; // stats grid = this many CTAs per SM (each CTA loops over slabs)
   int parts = 0;             // sub-batches run on internal streams (0 = auto, 1 = off, max 4)
+  int inline_members = 1;   // 1: member table inside the kernel parameters when the batch has <= 64 members
   int timing = 0;            // 1: bracket every kernel launch with CUDA events (bench.py roofline pass)
 };
 Options& options();

@@ -21,6 +21,7 @@
 //                      alignment -- the reference's two-pass path,
 //                      float/GpuFloatDecompress.cuh:622-694, is not needed).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -615,8 +616,8 @@ constexpr uint32_t kNoMember = 0xffffffffu;
 
 template <int KIND, int PB, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, DGB_DECODE_WARPS_PER_SM / WARPS)
-decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords, uint8_t* __restrict__ outSuccess,
-                  uint32_t* __restrict__ outSize, bool wantChecksum) {
+decodeFusedKernel(DecodeScratch sc, const __grid_constant__ InlineMembers im, uint32_t n, uint32_t slotWords,
+                  uint8_t* __restrict__ outSuccess, uint32_t* __restrict__ outSize, bool wantChecksum) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t K = 1u << PB;
   typedef typename Lut<PB, false>::Entry Entry;
@@ -653,7 +654,7 @@ decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords, uint8_t* __r
         uint32_t mm = cursor + lane;
         if (mm >= n) mm -= n;
         bool has = false;
-        if (tries + lane < n) has = *reinterpret_cast<volatile uint32_t*>(sc.next + mm) < __ldg(&sc.members[mm].work0);
+        if (tries + lane < n) has = *reinterpret_cast<volatile uint32_t*>(sc.next + mm) < memberWork0(im, sc.members, mm);
         const uint32_t mask = __ballot_sync(0xffffffffu, has);
         if (mask == 0u) {
           tries += 32u;
@@ -666,7 +667,7 @@ decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords, uint8_t* __r
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(sc.next + cand, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
-        if (c < __ldg(&sc.members[cand].work0)) {
+        if (c < memberWork0(im, sc.members, cand)) {
           pick = cand;
           firstBlock = c;
           cursor = cand;
@@ -680,7 +681,7 @@ decodeFusedKernel(DecodeScratch sc, uint32_t n, uint32_t slotWords, uint8_t* __r
     __syncthreads();
     const uint32_t m = sMisc[0];
     if (m == kNoMember) break;
-    const MemberDesc md = sc.members[m];
+    const MemberDesc md = memberAt(im, sc.members, m);
     const uint32_t blocksCap = md.work0;
 
     // ---- header(s), validity, LUT ----
@@ -857,6 +858,12 @@ int launchDecodeW(const DecodeScratch& sc, uint32_t m0, uint32_t m1, uint32_t pa
   return launchDecode<KIND, PB, 8, true, false>(sc, m0, m1, part, blockBound, stream);
 }
 
+// member table of the call in flight on this thread (decodeBatch fills it; count == 0: table in scratch)
+InlineMembers& decodeInline() {
+  static thread_local InlineMembers im;
+  return im;
+}
+
 template <int KIND, int PB, int WARPS>
 int launchDecodeFusedW(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
                        uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
@@ -885,7 +892,7 @@ int launchDecodeFusedW(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks
   const uint64_t resident = (uint64_t)perSm * smCountD();
   const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(resident, totalChunks));
   timerBegin(kSlotDecode, stream);
-  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, n, slotWords, outSuccess, outSize, checksum);
+  kern<<<grid, WARPS * 32, smemBytes, stream>>>(sc, decodeInline(), n, slotWords, outSuccess, outSize, checksum);
   DGB_CUDA_TRY(cudaGetLastError());
   timerEnd(kSlotDecode, stream);
   return DGB_OK;
@@ -971,7 +978,15 @@ int decodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   sc.checksum = reinterpret_cast<uint32_t*>(base + dp.checksum);
   sc.archiveChecksum = reinterpret_cast<uint32_t*>(base + dp.archiveChecksum);
   sc.sizes = reinterpret_cast<uint32_t*>(base + dp.sizes);
-  DGB_CUDA_TRY(cudaMemcpyAsync(sc.members, desc, sizeof(MemberDesc) * n, cudaMemcpyHostToDevice, stream));
+  // member table: inside the kernel parameters when it fits (the checksum pass reads it from scratch)
+  InlineMembers& im = decodeInline();
+  const bool inlined = opt.inline_members != 0 && fused && !checksum && n <= kInlineMembers;
+  im.count = inlined ? n : 0u;
+  if (inlined) {
+    std::memcpy(im.m, desc, sizeof(MemberDesc) * n);
+  } else {
+    DGB_CUDA_TRY(cudaMemcpyAsync(sc.members, desc, sizeof(MemberDesc) * n, cudaMemcpyHostToDevice, stream));
+  }
   if (checksum) DGB_CUDA_TRY(cudaMemsetAsync(sc.checksum, 0, 4 * (size_t)n, stream));
 
   if (fused) {

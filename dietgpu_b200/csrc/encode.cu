@@ -27,6 +27,7 @@
 // The archive produced is field-for-field the reference's (A.4 of SURVEY.md);
 // bits the reference leaves undefined are zero.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -191,12 +192,12 @@ __host__ __device__ inline uint32_t bytesSlabs(const void* in, uint32_t size, ui
 template <bool STAGED>
 __device__ __forceinline__ bool statsBytesItem(const EncodeScratch& sc, uint32_t (*sHist)[kNumSymbols],
                                                const uint32_t* __restrict__ histogramGiven, int pb,
-                                               bool useChecksum, uint32_t slabVecs, uint32_t m, uint32_t y,
+                                               bool useChecksum, uint32_t slabVecs, const MemberDesc& md,
+                                               uint32_t m, uint32_t y,
                                                uint32_t Y, uint32_t* __restrict__ outSize,
                                                const StatsStage& stage = StatsStage()) {
   // shuffle => the histogram base is provably warp-uniform (ATOMS [R + UR], no per-symbol add)
   const uint32_t t = threadIdx.x, warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const MemberDesc md = sc.members[m];
   const uint8_t* in = static_cast<const uint8_t*>(md.in);
   const uint32_t size = md.size;
   uint8_t* archive = static_cast<uint8_t*>(md.out);
@@ -279,10 +280,11 @@ __device__ __forceinline__ bool statsBytesItem(const EncodeScratch& sc, uint32_t
 }
 
 __global__ void __launch_bounds__(kStatsThreads)
-statsBytesKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven, int pb,
+statsBytesKernel(EncodeScratch sc, const __grid_constant__ InlineMembers im, const uint32_t* __restrict__ histogramGiven, int pb,
                  bool useChecksum, uint32_t slabVecs, uint32_t memberBase, uint32_t* __restrict__ outSize) {
   __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
-  statsBytesItem<false>(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y,
+  const uint32_t m = blockIdx.x + memberBase;
+  statsBytesItem<false>(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, memberAt(im, sc.members, m), m, blockIdx.y,
                         gridDim.y, outSize);
 }
 
@@ -370,14 +372,14 @@ __device__ __forceinline__ void histVectors(const uint4* __restrict__ vec, const
 // Work of CTA y of Y on member m; returns true in the CTA that finished the member.
 template <int FT, bool STAGED>
 __device__ __forceinline__ bool statsFloatItem(const EncodeScratch& sc, uint32_t (*sHist)[kNumSymbols], int pb,
-                                               bool useChecksum, uint32_t slabVecs, uint32_t m, uint32_t y,
+                                               bool useChecksum, uint32_t slabVecs, const MemberDesc& md,
+                                               uint32_t m, uint32_t y,
                                                uint32_t Y, uint32_t* __restrict__ outSize,
                                                const StatsStage& stage = StatsStage()) {
   constexpr uint32_t EPV = (FT == DGB_FLOAT32) ? 4u : 8u;  // elements per 16 B vector
   constexpr uint32_t WB = (FT == DGB_FLOAT32) ? 4u : 2u;   // word bytes
   // shuffle => the histogram base is provably warp-uniform (ATOMS [R + UR], no per-symbol add)
   const uint32_t t = threadIdx.x, warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const MemberDesc md = sc.members[m];
   const uint8_t* in = static_cast<const uint8_t*>(md.in);
   const uint32_t size = md.size;  // float words
   uint8_t* archive = static_cast<uint8_t*>(md.out);
@@ -468,10 +470,12 @@ __device__ __forceinline__ bool statsFloatItem(const EncodeScratch& sc, uint32_t
 
 template <int FT>
 __global__ void __launch_bounds__(kStatsThreads)
-statsFloatKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slabVecs, uint32_t memberBase,
-                 uint32_t* __restrict__ outSize) {
+statsFloatKernel(EncodeScratch sc, const __grid_constant__ InlineMembers im, int pb, bool useChecksum, uint32_t slabVecs,
+                 uint32_t memberBase, uint32_t* __restrict__ outSize) {
   __shared__ uint32_t sHist[kStatsWarps][kNumSymbols];
-  statsFloatItem<FT, false>(sc, sHist, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y, gridDim.y, outSize);
+  const uint32_t m = blockIdx.x + memberBase;
+  statsFloatItem<FT, false>(sc, sHist, pb, useChecksum, slabVecs, memberAt(im, sc.members, m), m, blockIdx.y, gridDim.y,
+                            outSize);
 }
 
 // K1 with the slab landed in shared memory by one TMA bulk copy per CTA (option stats_stage): the
@@ -493,8 +497,8 @@ statsFloatStagedKernel(EncodeScratch sc, int pb, bool useChecksum, uint32_t slab
   if (threadIdx.x == 0) mbarInit(stage.bar, 1);
   fenceBarrierInit();
   __syncthreads();
-  statsFloatItem<FT, true>(sc, sHist, pb, useChecksum, slabVecs, blockIdx.x + memberBase, blockIdx.y, gridDim.y, outSize,
-                           stage);
+  const uint32_t m = blockIdx.x + memberBase;
+  statsFloatItem<FT, true>(sc, sHist, pb, useChecksum, slabVecs, sc.members[m], m, blockIdx.y, gridDim.y, outSize, stage);
 }
 
 // ---------------------------------------------------------------------------
@@ -1247,7 +1251,7 @@ __device__ __forceinline__ void encodeMemberBlocks(const EncodeScratch& sc, cons
 
 template <bool WIDE, int KIND>
 __global__ void
-encodeKernelFast(EncodeScratch sc, int pb, bool useChecksum,
+encodeKernelFast(EncodeScratch sc, const __grid_constant__ InlineMembers im, int pb, bool useChecksum,
                                  uint32_t numMembers, uint32_t blockBegin, uint32_t blockEnd,
                                  uint32_t slotWords, uint32_t spillWarpBase,
                                  uint32_t* __restrict__ outSize) {
@@ -1274,13 +1278,13 @@ encodeKernelFast(EncodeScratch sc, int pb, bool useChecksum,
       uint32_t lo = 0, hi = numMembers;
       while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&sc.members[mid].work0) <= cur) lo = mid; else hi = mid;
+        if (memberWork0(im, sc.members, mid) <= cur) lo = mid; else hi = mid;
       }
       sMember = lo;
     }
     __syncthreads();
     const uint32_t m = sMember;
-    const MemberDesc md = sc.members[m];
+    const MemberDesc md = memberAt(im, sc.members, m);
     const uint32_t nb = divUp(md.size, kBlockBytes);
     const uint32_t memberEnd = min(end, md.work0 + nb);
     loadTable<WIDE>(sc, sTab, m);
@@ -1399,11 +1403,11 @@ encodeFusedKernel(EncodeScratch sc, const uint32_t* __restrict__ histogramGiven,
       const uint2 w0 = __ldg(&sc.workIdx[m]), w1 = __ldg(&sc.workIdx[m + 1]);
       bool finished;
       if (KIND == kKindBytes) {
-        finished = statsBytesItem<STAGED>(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, m, arg - w0.x,
+        finished = statsBytesItem<STAGED>(sc, sHist, histogramGiven, pb, useChecksum, slabVecs, sc.members[m], m, arg - w0.x,
                                           w1.x - w0.x, outSize, stage);
       } else {
         finished = statsFloatItem<KIND == kKindBytes ? DGB_FLOAT16 : KIND, STAGED>(
-            sc, sHist, pb, useChecksum, slabVecs, m, arg - w0.x, w1.x - w0.x, outSize, stage);
+            sc, sHist, pb, useChecksum, slabVecs, sc.members[m], m, arg - w0.x, w1.x - w0.x, outSize, stage);
       }
       if (finished) {
         // table, pdf and (through the ticket chain) every comp / stored byte of the member are
@@ -1577,15 +1581,15 @@ struct K2Launcher {
     return DGB_OK;
   }
   static void launch(int variant, uint32_t grid, uint32_t W, size_t smemBytes, cudaStream_t ps, const EncodeScratch& sc,
-                     int pb, bool checksum, uint32_t n, uint32_t totalTickets, uint32_t blockBegin, uint32_t blockEnd,
+                     const InlineMembers& im, int pb, bool checksum, uint32_t n, uint32_t totalTickets, uint32_t blockBegin, uint32_t blockEnd,
                      uint32_t slotWords, uint32_t spillWarpBase, uint32_t* outSize_dev) {
     if (variant == 0) {
       encodeKernel<KIND><<<grid, W * 32, smemBytes, ps>>>(sc, pb, checksum, n, totalTickets, outSize_dev);
     } else if (variant == 1) {
-      encodeKernelFast<false, KIND><<<grid, W * 32, smemBytes, ps>>>(sc, pb, checksum, n, blockBegin, blockEnd, slotWords,
+      encodeKernelFast<false, KIND><<<grid, W * 32, smemBytes, ps>>>(sc, im, pb, checksum, n, blockBegin, blockEnd, slotWords,
                                                                     spillWarpBase, outSize_dev);
     } else {
-      encodeKernelFast<true, KIND><<<grid, W * 32, smemBytes, ps>>>(sc, pb, checksum, n, blockBegin, blockEnd, slotWords,
+      encodeKernelFast<true, KIND><<<grid, W * 32, smemBytes, ps>>>(sc, im, pb, checksum, n, blockBegin, blockEnd, slotWords,
                                                                    spillWarpBase, outSize_dev);
     }
   }
@@ -1685,7 +1689,16 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
   sc.spill = base + sp.spill;
   sc.table = reinterpret_cast<uint4*>(base + sp.table);
 
-  DGB_CUDA_TRY(cudaMemcpyAsync(base + sp.members, hs.upload.data(), hs.upload.size(), cudaMemcpyHostToDevice, stream));
+  // member table: inside the kernel parameters when it fits and the default kernels run, else one upload
+  static thread_local InlineMembers im;
+  const bool inlined = opt.inline_members != 0 && n <= kInlineMembers && !fused && !canonical &&
+                       !(kind != kKindBytes && opt.stats_stage != 0);
+  im.count = inlined ? n : 0u;
+  if (inlined) {
+    std::memcpy(im.m, desc, descBytes);
+  } else {
+    DGB_CUDA_TRY(cudaMemcpyAsync(base + sp.members, hs.upload.data(), hs.upload.size(), cudaMemcpyHostToDevice, stream));
+  }
   DGB_CUDA_TRY(cudaMemsetAsync(base + sp.zeroBegin, 0, (canonical ? sp.lookbackEnd : sp.zeroEnd) - sp.zeroBegin, stream));
 
   const int sms = smCount();
@@ -1789,13 +1802,13 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
         statsFloatStagedKernel<DGB_FLOAT32><<<grid1, kStatsThreads, stageBytes, ps>>>(sc, pb, checksum, slabVecsK1, m0, outSize_dev);
       }
     } else if (kind == kKindBytes) {
-      statsBytesKernel<<<grid1, kStatsThreads, 0, ps>>>(sc, histogram_dev, pb, checksum, slabVecs, m0, outSize_dev);
+      statsBytesKernel<<<grid1, kStatsThreads, 0, ps>>>(sc, im, histogram_dev, pb, checksum, slabVecs, m0, outSize_dev);
     } else if (kind == kKindF16) {
-      statsFloatKernel<DGB_FLOAT16><<<grid1, kStatsThreads, 0, ps>>>(sc, pb, checksum, slabVecs, m0, outSize_dev);
+      statsFloatKernel<DGB_FLOAT16><<<grid1, kStatsThreads, 0, ps>>>(sc, im, pb, checksum, slabVecs, m0, outSize_dev);
     } else if (kind == kKindBF16) {
-      statsFloatKernel<DGB_BFLOAT16><<<grid1, kStatsThreads, 0, ps>>>(sc, pb, checksum, slabVecs, m0, outSize_dev);
+      statsFloatKernel<DGB_BFLOAT16><<<grid1, kStatsThreads, 0, ps>>>(sc, im, pb, checksum, slabVecs, m0, outSize_dev);
     } else {
-      statsFloatKernel<DGB_FLOAT32><<<grid1, kStatsThreads, 0, ps>>>(sc, pb, checksum, slabVecs, m0, outSize_dev);
+      statsFloatKernel<DGB_FLOAT32><<<grid1, kStatsThreads, 0, ps>>>(sc, im, pb, checksum, slabVecs, m0, outSize_dev);
     }
     DGB_CUDA_TRY(cudaGetLastError());
     timerEnd(kSlotStats, ps);
@@ -1816,7 +1829,7 @@ int encodeBatch(int kind, void* temp, size_t tempBytes, int pb, bool checksum, u
         grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, resident));
         grid2 = std::max(1u, std::min(grid2, spillWarpsPerPart / W));  // every warp owns a spill slot
       }
-      DGB_BY_KIND(kind, launch(variant, grid2, W, smemBytes, ps, sc, pb, checksum, n, totalTickets, blockBegin, blockEnd,
+      DGB_BY_KIND(kind, launch(variant, grid2, W, smemBytes, ps, sc, im, pb, checksum, n, totalTickets, blockBegin, blockEnd,
                                slotWords, (uint32_t)part * spillWarpsPerPart, outSize_dev));
       DGB_CUDA_TRY(cudaGetLastError());
       timerEnd(kSlotEncode, ps);

@@ -467,7 +467,7 @@ def test_kernel_variants_agree():
     a = [zipf_bytes(300000, 1.1, 5), exp_bytes(4097, 50, 6), zipf_bytes(1, 1.0, 7), np.zeros(0, np.uint8)]
     f = [normal_words(50000 + 13 * i, "bf16", i) for i in range(5)]
     names = ("encode_fused", "decode_fused", "fused_chunk_blocks", "fused_stats_every", "fused_stage",
-             "encode_warps", "encode_canonical")
+             "encode_warps", "encode_canonical", "inline_members")
     defaults = {k: capi.get_option(k) for k in names}
     variants = [
         dict(encode_fused=0, decode_fused=0),
@@ -483,6 +483,7 @@ def test_kernel_variants_agree():
         dict(encode_fused=0, encode_warps=4),
         dict(encode_canonical=1),
         dict(encode_canonical=1, decode_fused=0),
+        dict(inline_members=0),  # member table uploaded to scratch instead of travelling in the kernel parameters
     ]
     try:
         for v in variants:
@@ -493,6 +494,49 @@ def test_kernel_variants_agree():
     finally:
         for k, d in defaults.items():
             capi.set_option(k, d)
+
+
+def test_more_members_than_fit_the_kernel_parameters():
+    # batches above 64 members read the member table from scratch, up to 64 from the kernel parameters:
+    # both sides of the boundary, bytes and floats, against the oracle
+    for n in (63, 64, 65, 130):
+        ans_roundtrip([zipf_bytes(3000 + 37 * i, 1.2, i) for i in range(n)], 10)
+        float_roundtrip("f16", [normal_words(2500 + 11 * i, "f16", i) for i in range(n)], 10)
+
+
+def test_calls_can_be_captured_into_a_cuda_graph():
+    # with the member table in the kernel parameters a call reads no host memory after it returns, so
+    # compress + decompress can be captured once and replayed on new data in the same buffers
+    from dietgpu_b200 import ops
+
+    n, per = 6, 40000 + 17
+    ts = [torch.zeros(per, dtype=torch.bfloat16, device="cuda") for _ in range(n)]
+    outs = [torch.empty_like(t) for t in ts]
+    _, cols = ops.max_float_compressed_output_size(ts)
+    comp = torch.empty((n, cols), dtype=torch.uint8, device="cuda")
+    sizes = torch.zeros(n, dtype=torch.int32, device="cuda")
+    temp = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    rows = [comp[i] for i in range(n)]
+
+    def step():
+        ops.compress_data(True, ts, False, temp, comp, sizes)
+        ops.decompress_data(True, rows, outs, False, temp)
+
+    step()  # warm-up outside capture (function attributes, occupancy queries)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    for seed in (1, 2, 3):
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        for t in ts:
+            t.copy_(torch.randn(per, generator=gen, device="cuda").to(torch.bfloat16) * (seed * 3.0))
+        g.replay()
+        torch.cuda.synchronize()
+        for t, o in zip(ts, outs):
+            assert torch.equal(t.view(torch.int16), o.view(torch.int16))
+        want = [len(O.float_compress(O.BF16, t.view(torch.int16).cpu().numpy().view(np.uint16), 10)) for t in ts]
+        assert sizes.cpu().tolist() == want
 
 
 def test_get_compressed_info_matches_oracle():

@@ -23,6 +23,8 @@ def _worker(rank, world, port, backend, q):
         import dietgpu_b200 as dg
 
         ok = True
+        # peer-memory transport (NVLink pull by the decode kernel): needs one GPU per rank
+        ws = dg.PeerWorkspace(4 << 20) if backend == "nccl" else None
         for dt, n in ((torch.bfloat16, 300001), (torch.float16, 70000), (torch.uint8, 123457)):
             def make(r):
                 g = torch.Generator(device="cpu").manual_seed(1000 + r)
@@ -46,6 +48,20 @@ def _worker(rank, world, port, backend, q):
             recv = dg.all_to_all_compressed([chunk(rank, d).to(dev) for d in range(world)])
             for s in range(world):
                 ok = ok and torch.equal(recv[s].view(torch.uint8), chunk(s, rank).to(dev).view(torch.uint8))
+            if ws is not None:
+                for _ in range(3):  # both halves of the workspace, and a reuse
+                    got = dg.all_gather_compressed(mine, members=6, peer=ws)
+                    ok = ok and torch.equal(got.view(torch.uint8), want.view(torch.uint8))
+
+                def reg(src, dst):  # regular all-to-all: one length
+                    g = torch.Generator(device="cpu").manual_seed(99 + 10 * src + dst)
+                    if dt.is_floating_point:
+                        return torch.randn(40001, generator=g).to(dt)
+                    return torch.randint(0, 9, (40001,), generator=g, dtype=torch.int32).to(dt)
+
+                recv = dg.all_to_all_compressed([reg(rank, d).to(dev) for d in range(world)], peer=ws)
+                for s in range(world):
+                    ok = ok and torch.equal(recv[s].view(torch.uint8), reg(s, rank).to(dev).view(torch.uint8))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

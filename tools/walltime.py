@@ -43,5 +43,33 @@ for v in sys.argv[2:] or [""]:
     e[2].record()
     torch.cuda.synchronize()
     te, td = e[0].elapsed_time(e[1]) / n * 1e3, e[1].elapsed_time(e[2]) / n * 1e3
-    print(f"{wl} [{v}] ok={ok} enc {te:.1f}us {ub / te / 1e3:.0f} GB/s | dec {td:.1f}us {ub / td / 1e3:.0f} GB/s | both {2 * ub / (te + td) / 1e3:.0f} GB/s", flush=True)
+    # the bench's step: encode and decode alternate on one stream
+    e[0].record()
+    for _ in range(n):
+        c.encode(); c.decode()
+    e[1].record()
+    torch.cuda.synchronize()
+    ts_ = e[0].elapsed_time(e[1]) / n * 1e3
+    # the same step captured once into a CUDA graph and replayed (possible when the member table travels in the
+    # kernel parameters: nothing of the call reads host memory later)
+    tg = float("nan")
+    if os.environ.get("WALL_GRAPH", "1") == "1":
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                c.encode(); c.decode()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e[0].record()
+            for _ in range(n):
+                g.replay()
+            e[1].record()
+            torch.cuda.synchronize()
+            tg = e[0].elapsed_time(e[1]) / n * 1e3
+            ok = ok and all(torch.equal(a.view(it), b.view(it)) for a, b in zip(ts, c.outs))
+        except Exception as ex:  # noqa: BLE001
+            print("graph capture failed:", str(ex)[:200])
+    print(f"{wl} [{v}] ok={ok} enc {te:.1f}us {ub / te / 1e3:.0f} GB/s | dec {td:.1f}us {ub / td / 1e3:.0f} GB/s | both {2 * ub / (te + td) / 1e3:.0f} GB/s"
+          f" | step {ts_:.1f}us {2 * ub / ts_ / 1e3:.0f} GB/s | graph step {tg:.1f}us {2 * ub / tg / 1e3:.0f} GB/s", flush=True)
     del c
