@@ -27,7 +27,7 @@ SYMBOLS = [
     "dgb_float_compress_pointer", "dgb_float_compress_split_size",
     "dgb_float_decompress_pointer", "dgb_float_decompress_split_size",
     "dgb_float_get_compressed_info",
-    "dgb_copy_async", "dgb_copy_rows_async",
+    "dgb_copy_async", "dgb_copy_rows_async", "dgb_archives_pull",
     "dgb_set_option", "dgb_get_option", "dgb_kernel_times",
 ]
 
@@ -100,6 +100,8 @@ def lib():
     L.dgb_copy_async.argtypes = [vp, vp, sz, vp]
     L.dgb_copy_rows_async.restype = i32
     L.dgb_copy_rows_async.argtypes = [vp, sz, vp, sz, sz, sz, vp]
+    L.dgb_archives_pull.restype = i32
+    L.dgb_archives_pull.argtypes = [i32, u32, vp, vp, vp, vp, vp]
     L.dgb_kernel_times.restype = i32
     L.dgb_kernel_times.argtypes = [vp, vp, i32]
     _lib = L
@@ -133,7 +135,7 @@ def u32_array(vals):
     return (C.c_uint32 * len(vals))(*[int(v) for v in vals])
 
 
-KERNEL_SLOTS = ["stats", "encode", "plan", "decode", "checksum", "encode_fused"]
+KERNEL_SLOTS = ["stats", "encode", "plan", "decode", "checksum", "encode_fused", "pull"]
 
 
 def kernel_times():

@@ -140,7 +140,10 @@ class PeerWorkspace:
         self.hdl = symm.rendezvous(self.buf, self.group)
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.calls = 0
+        self.timeout_ms = 20000
         self._views = {}
+        self._staging = None
+        self.side = torch.cuda.Stream(device=dev)  # archive mover: runs beside the decoder
 
     def begin(self, nbytes: int) -> int:
         """Byte offset of the half this call uses."""
@@ -160,9 +163,23 @@ class PeerWorkspace:
             v = self._views[key] = self.hdl.get_buffer(rank, (nbytes,), torch.uint8, offset)
         return v
 
+    def staging(self, nbytes: int) -> torch.Tensor:
+        """Local (not peer-mapped) buffer the archive mover fills; grown on demand, kept across calls."""
+        if self._staging is None or self._staging.numel() < nbytes:
+            self._staging = torch.empty(nbytes, dtype=torch.uint8, device=self.buf.device)
+        return self._staging[:nbytes]
+
     def barrier(self) -> None:
         """Device-side barrier of all ranks on the current stream (no host synchronisation)."""
         self.hdl.barrier(channel=0)
+
+    # point-to-point flags on the current stream (channel 0 belongs to barrier()); a lost signal traps the
+    # waiting kernel after `timeout_ms` instead of hanging the device
+    def signal(self, dst: int, channel: int) -> None:
+        self.hdl.put_signal(dst, channel=channel, timeout_ms=self.timeout_ms)
+
+    def wait(self, src: int, channel: int) -> None:
+        self.hdl.wait_signal(src, channel=channel, timeout_ms=self.timeout_ms)
 
 
 def _archive_cols(as_float: bool, dtype: torch.dtype, longest: int) -> int:
@@ -171,8 +188,96 @@ def _archive_cols(as_float: bool, dtype: torch.dtype, longest: int) -> int:
     return _round_up(int(b), _ALIGN)
 
 
-def _all_gather_peer(flat: torch.Tensor, as_float: bool, bounds: List[int], ws: PeerWorkspace, checksum: bool,
-                     temp_mem: Optional[torch.Tensor], check: bool) -> torch.Tensor:
+def _pull_and_decode(ws: "PeerWorkspace", as_float: bool, dtype: torch.dtype, units, cols: int, checksum: bool,
+                     temp_mem: Optional[torch.Tensor], check: bool, direct: bool) -> None:
+    """units = [(source rows [k, cols] in peer memory, [k output tensors]), ...].  direct: the decode kernel reads
+    the peer rows itself.  Otherwise a two-deep pipeline: the archive mover (dgb_archives_pull, a small grid on
+    the workspace's side stream) brings unit u+1 into local staging while the decoder works on unit u."""
+    dev = units[0][1][0].device
+    statuses = []
+    if direct:
+        ins = [rows[i] for rows, outs in units for i in range(len(outs))]
+        outs = [o for _, os_ in units for o in os_]
+        st = torch.zeros(len(ins), dtype=torch.uint8, device=dev)
+        ops.decompress_data(as_float, ins, outs, checksum, temp_mem, st)
+        statuses.append(st)
+    else:
+        cur = torch.cuda.current_stream(dev)
+        kmax = max(len(outs) for _, outs in units)
+        stage = ws.staging(2 * kmax * cols).view(2, kmax, cols)
+        start = torch.cuda.Event()
+        start.record(cur)
+        ws.side.wait_event(start)
+        decoded = [None, None]  # event: the decoder is done with staging buffer b
+        for u, (rows, outs) in enumerate(units):
+            b, k = u & 1, len(outs)
+            with torch.cuda.stream(ws.side):
+                if decoded[b] is not None:
+                    ws.side.wait_event(decoded[b])
+                ops.pull_archives(as_float, [rows[i] for i in range(k)], [stage[b, i] for i in range(k)], dtype)
+                pulled = torch.cuda.Event()
+                pulled.record(ws.side)
+            cur.wait_event(pulled)
+            st = torch.zeros(k, dtype=torch.uint8, device=dev)
+            ops.decompress_data(as_float, [stage[b, i] for i in range(k)], outs, checksum, temp_mem, st)
+            statuses.append(st)
+            decoded[b] = torch.cuda.Event()
+            decoded[b].record(cur)
+    if check and not all(bool(st.all()) for st in statuses):
+        raise RuntimeError("compressed collective: a peer archive failed to decode")
+
+
+def _all_gather_push(flat: torch.Tensor, as_float: bool, bounds: List[int], ws: "PeerWorkspace", checksum: bool,
+                     temp_mem: Optional[torch.Tensor], check: bool, stages: int) -> torch.Tensor:
+    """Push transport: the members are coded in `stages` groups; as soon as a group is coded, the archive mover
+    (side stream) WRITES its archives into every peer's inbox -- stores over NVLink are posted, they do not pay the
+    round trip a pull does -- and raises a flag there; the receiver decodes a group from its own memory when the
+    flag is up.  Coding of group g+1, the pushes of group g and the decoding of what has arrived overlap; there is
+    no barrier: the flags of call k+1 order every rank's reads of call k before the writes of call k+2."""
+    n, members, world, rank = flat.numel(), len(bounds) - 1, ws.world, ws.rank
+    dev = flat.device
+    cols = _archive_cols(as_float, flat.dtype, max(bounds[i + 1] - bounds[i] for i in range(members)))
+    region = members * cols
+    off = ws.begin((world + 1) * region)  # [own archives | inbox of source 0 | ... | inbox of source world-1]
+    out = torch.empty(world * n, dtype=flat.dtype, device=dev)
+    mine = ws.view(rank, off, region).view(members, cols)
+    stages = max(1, min(int(stages), members, 7))
+    cuts = [round(k * members / stages) for k in range(stages + 1)]
+    groups = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    cur = torch.cuda.current_stream(dev)
+    peers = [(rank + k) % world for k in range(1, world)]
+    sizes = torch.empty(members, dtype=torch.int32, device=dev)
+    for g, (a, b) in enumerate(groups):
+        ops.compress_data(as_float, [flat[bounds[i]:bounds[i + 1]] for i in range(a, b)], checksum, temp_mem, mine[a:b], sizes[a:b])
+        coded = torch.cuda.Event()
+        coded.record(cur)
+        with torch.cuda.stream(ws.side):
+            ws.side.wait_event(coded)
+            for p in peers:
+                inbox = ws.view(p, off + (1 + rank) * region, region).view(members, cols)
+                ops.pull_archives(as_float, [mine[i] for i in range(a, b)], [inbox[i] for i in range(a, b)], flat.dtype)
+                ws.signal(p, 1 + g)
+    out[rank * n:(rank + 1) * n].copy_(flat)  # own shard: a local copy, no codec
+    statuses = []
+    for g, (a, b) in enumerate(groups):
+        for src in reversed(peers):  # rank - 1 pushed to this rank first
+            ws.wait(src, 1 + g)
+            rows = ws.view(rank, off + (1 + src) * region, region).view(members, cols)
+            st = torch.zeros(b - a, dtype=torch.uint8, device=dev)
+            ops.decompress_data(as_float, [rows[i] for i in range(a, b)],
+                                [out[src * n + bounds[i]: src * n + bounds[i + 1]] for i in range(a, b)], checksum, temp_mem, st)
+            statuses.append(st)
+    done = torch.cuda.Event()
+    with torch.cuda.stream(ws.side):
+        done.record(ws.side)
+    cur.wait_event(done)  # the side stream joins (stream capture needs it; the next call's scratch reuse too)
+    if check and not all(bool(st.all()) for st in statuses):
+        raise RuntimeError("all_gather_compressed: a peer archive failed to decode")
+    return out
+
+
+def _all_gather_peer(flat: torch.Tensor, as_float: bool, bounds: List[int], ws: "PeerWorkspace", checksum: bool,
+                     temp_mem: Optional[torch.Tensor], check: bool, direct: bool, stages: int) -> torch.Tensor:
     n, members, world, rank = flat.numel(), len(bounds) - 1, ws.world, ws.rank
     cols = _archive_cols(as_float, flat.dtype, max(bounds[i + 1] - bounds[i] for i in range(members)))
     off = ws.begin(members * cols)
@@ -182,18 +287,17 @@ def _all_gather_peer(flat: torch.Tensor, as_float: bool, bounds: List[int], ws: 
     ops.compress_data(as_float, [flat[bounds[i]:bounds[i + 1]] for i in range(members)], checksum, temp_mem, mine, sizes)
     ws.barrier()  # every rank's archives are complete (and every rank is done with the previous call's other half)
     out[rank * n:(rank + 1) * n].copy_(flat)  # own shard: a local copy, no codec
-    ins, outs = [], []
+    stages = max(1, min(int(stages), members))
+    cuts = [round(k * members / stages) for k in range(stages + 1)]
+    units = []
     for k in range(1, world):
         w = (rank + k) % world  # start with a different peer on every rank: spreads the pulls over the links
         rows = ws.view(w, off, members * cols).view(members, cols)
-        for i in range(members):
-            ins.append(rows[i])
-            outs.append(out[w * n + bounds[i]: w * n + bounds[i + 1]])
-    if ins:
-        status = torch.zeros(len(ins), dtype=torch.uint8, device=flat.device)
-        ops.decompress_data(as_float, ins, outs, checksum, temp_mem, status)
-        if check and not bool(status.all()):
-            raise RuntimeError("all_gather_compressed: a peer archive failed to decode")
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b > a:
+                units.append((rows[a:b], [out[w * n + bounds[i]: w * n + bounds[i + 1]] for i in range(a, b)]))
+    if units:
+        _pull_and_decode(ws, as_float, flat.dtype, units, cols, checksum, temp_mem, check, direct)
     return out
 
 
@@ -206,14 +310,17 @@ def _split(n: int, parts: int, quantum: int) -> List[int]:
 
 def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksum: bool = False,
                           temp_mem: Optional[torch.Tensor] = None, stages: int = 2,
-                          peer: Optional[PeerWorkspace] = None, check: bool = True) -> torch.Tensor:
+                          peer: Optional[PeerWorkspace] = None, check: bool = True,
+                          peer_mode: str = "push") -> torch.Tensor:
     """Every rank contributes the CUDA tensor `t` (same shape and dtype on every rank; fp16 / bf16 / fp32 go
     through the float codec, anything else through the byte codec) and receives the concatenation
     [world * t.numel()] in rank order, bit-exact.  `members` = archives per rank (the codec's parallelism
     comes from blocks, so a handful is enough); `stages` = pipeline pieces (see the module docstring).
-    With `peer` (a PeerWorkspace of the same group) the archives are pulled over NVLink by the decode kernel
-    instead of being exchanged by a collective; `check=False` then skips the only host synchronisation (the
-    read of the decode status)."""
+    With `peer` (a PeerWorkspace of the same group) the archives move through peer-mapped memory instead of a
+    collective; `peer_mode` = "push" (the archive mover writes each coded group into the peers' inboxes and flags
+    it), "pull" (after a barrier the mover reads the peers' archives, unit u+1 while unit u is decoded) or
+    "direct" (after a barrier the decode kernel reads peer memory itself); `stages` = pipeline groups;
+    `check=False` then skips the only host synchronisation (the read of the decode status)."""
     if not t.is_cuda or not t.is_contiguous():
         raise ValueError("all_gather_compressed: contiguous CUDA tensor expected (no CPU fallback)")
     as_float = t.dtype in (torch.float16, torch.bfloat16, torch.float32)
@@ -224,7 +331,12 @@ def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksu
     bounds = _split(n, members, 8)
     members = len(bounds) - 1
     if peer is not None:
-        out = _all_gather_peer(flat, as_float, bounds, peer, checksum, temp_mem, check)
+        if peer_mode not in ("push", "pull", "direct"):
+            raise ValueError("all_gather_compressed: peer_mode is 'push', 'pull' or 'direct'")
+        if peer_mode == "push":
+            out = _all_gather_push(flat, as_float, bounds, peer, checksum, temp_mem, check, stages)
+        else:
+            out = _all_gather_peer(flat, as_float, bounds, peer, checksum, temp_mem, check, peer_mode == "direct", stages)
         return out if as_float else out.view(t.dtype)
     world = _world(group)
     out = torch.empty(world * n, dtype=flat.dtype, device=t.device)
@@ -268,7 +380,7 @@ def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksu
 
 
 def _all_to_all_peer(flats: List[torch.Tensor], as_float: bool, ws: PeerWorkspace, checksum: bool,
-                     temp_mem: Optional[torch.Tensor], check: bool) -> List[torch.Tensor]:
+                     temp_mem: Optional[torch.Tensor], check: bool, direct: bool) -> List[torch.Tensor]:
     """Regular all-to-all (chunk (s, d) has the same length on every rank pair): rank r encodes its chunks as one
     batch into its own peer-mapped rows, and after the barrier decodes row [r] of every peer straight out of
     the peer's memory."""
@@ -284,19 +396,18 @@ def _all_to_all_peer(flats: List[torch.Tensor], as_float: bool, ws: PeerWorkspac
     ws.barrier()
     outs = [torch.empty(m, dtype=flats[0].dtype, device=dev) for _ in range(world)]
     outs[rank].copy_(flats[rank])
-    order = [(rank + k) % world for k in range(1, world)]
-    ins = [ws.view(s, off + rank * cols, cols) for s in order]
-    if order:
-        status = torch.zeros(len(order), dtype=torch.uint8, device=dev)
-        ops.decompress_data(as_float, ins, [outs[s] for s in order], checksum, temp_mem, status)
-        if check and not bool(status.all()):
-            raise RuntimeError("all_to_all_compressed: a peer archive failed to decode")
+    units = []
+    for k in range(1, world):
+        src = (rank + k) % world
+        units.append((ws.view(src, off + rank * cols, cols).view(1, cols), [outs[src]]))
+    if units:
+        _pull_and_decode(ws, as_float, flats[0].dtype, units, cols, checksum, temp_mem, check, direct)
     return outs
 
 
 def all_to_all_compressed(chunks: Sequence[torch.Tensor], group=None, checksum: bool = False,
                           temp_mem: Optional[torch.Tensor] = None, peer: Optional[PeerWorkspace] = None,
-                          check: bool = True) -> List[torch.Tensor]:
+                          check: bool = True, peer_mode: str = "pull") -> List[torch.Tensor]:
     """chunks[d] (CUDA, contiguous, same dtype and shape on every rank for a given (source, destination) pair is
     NOT required: sizes travel with the data) goes to rank d; returns [world] tensors, entry s = what rank s
     sent here, bit-exact.  One archive per destination; the payload moves with all_to_all_single and exact
@@ -311,7 +422,7 @@ def all_to_all_compressed(chunks: Sequence[torch.Tensor], group=None, checksum: 
     as_float = dt in (torch.float16, torch.bfloat16, torch.float32)
     flats = [c.reshape(-1) if as_float else c.reshape(-1).view(torch.uint8) for c in chunks]
     if peer is not None:
-        outs = _all_to_all_peer(flats, as_float, peer, checksum, temp_mem, check)
+        outs = _all_to_all_peer(flats, as_float, peer, checksum, temp_mem, check, peer_mode == "direct")
         return [x if as_float else x.view(dt) for x in outs]
     comp, sizes, _ = ops.compress_data(as_float, flats, checksum, temp_mem)
     if world == 1:

@@ -372,6 +372,13 @@ int dgb_copy_rows_async(void* dst, size_t dst_pitch, const void* src, size_t src
   return DGB_OK;
 }
 
+int dgb_archives_pull(int float_type, uint32_t num_in_batch, const void* const* src, void* const* dst,
+                      const uint32_t* dst_capacity, uint32_t* out_bytes_dev, void* stream) {
+  if (float_type != 0 && float_type != DGB_FLOAT16 && float_type != DGB_BFLOAT16 && float_type != DGB_FLOAT32)
+    return DGB_ERR_INVALID_ARG;
+  return dgb::pullArchives(float_type, num_in_batch, src, dst, dst_capacity, out_bytes_dev, (cudaStream_t)stream);
+}
+
 // ---- options ---------------------------------------------------------------
 
 static int* optionSlot(const char* name) {
@@ -394,6 +401,7 @@ static int* optionSlot(const char* name) {
   if (!std::strcmp(name, "hist_slab_kb")) return &o.hist_slab_kb;
   if (!std::strcmp(name, "hist_ctas_per_sm")) return &o.hist_ctas_per_sm;
   if (!std::strcmp(name, "inline_members")) return &o.inline_members;
+  if (!std::strcmp(name, "pull_ctas")) return &o.pull_ctas;
   if (!std::strcmp(name, "timing")) return &o.timing;
   if (!std::strcmp(name, "parts")) return &o.parts;
   return nullptr;

@@ -106,6 +106,7 @@ struct Options {
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_ctas_per_sm = 32; // stats grid = this many CTAs per SM (each CTA loops over slabs)
   int parts = 0;             // sub-batches run on internal streams (0 = auto, 1 = off, max 4)
+  int pull_ctas = 64;        // grid of the archive mover (dgb_archives_pull): enough loads in flight for NVLink, few SMs
   int inline_members = 1;   // 1: member table inside the kernel parameters when the batch has <= 64 members
   int timing = 0;            // 1: bracket every kernel launch with CUDA events (bench.py roofline pass)
 };
@@ -129,12 +130,14 @@ size_t decodeTempBytes(int kind, uint32_t n);
 int getInfo(int kind, void* temp, size_t tempBytes, const void* const* in, bool inIsDevice,
             uint32_t n, uint32_t* outSizes, uint32_t* outTypes, uint32_t* outChecksum,
             cudaStream_t stream);
+int pullArchives(int kind, uint32_t n, const void* const* src, void* const* dst, const uint32_t* capacity,
+                 uint32_t* outBytes_dev, cudaStream_t stream);
 
 void setLastCudaError(cudaError_t e);
 
 // Per-kernel timing (options().timing): slots are stable indices reported by
 // dgb_kernel_times().  No-ops when timing is off.
-enum TimerSlot : int { kSlotStats = 0, kSlotEncode = 1, kSlotPlan = 2, kSlotDecode = 3, kSlotChecksum = 4, kSlotFused = 5, kNumSlots = 6 };
+enum TimerSlot : int { kSlotStats = 0, kSlotEncode = 1, kSlotPlan = 2, kSlotDecode = 3, kSlotChecksum = 4, kSlotFused = 5, kSlotPull = 6, kNumSlots = 7 };
 // Internal helper streams: a large batch is cut into up to kMaxParts contiguous sub-batches whose
 // kernels run on separate streams (forked from / joined to the caller's stream with events), so the
 // HBM-bound and the issue-bound kernels of different sub-batches overlap and launch gaps hide.

@@ -1100,6 +1100,99 @@ __global__ void infoKernel(int kind, const void* const* in, uint32_t n, uint32_t
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// Archive mover: copies each archive EXACTLY as long as its own header says (float header + stored planes +
+// ANS header .. data section), never the padded row it sits in.  Meant for sources in peer memory
+// (NVLink): the sizes never travel to the host, every thread keeps four 16 B loads in flight, and a
+// small persistent grid (option "pull_ctas") saturates the link while the decode kernel of the
+// previous group owns the rest of the SMs.  An archive with a bad header is copied as its first 32
+// bytes, so the decoder that follows reports it; one that exceeds the destination capacity is cut
+// (the decoder then fails its bounds checks on the member, never reads past the row).
+// ---------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ uint4 ldgNc(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+constexpr uint32_t kPullThreads = 512;
+constexpr uint32_t kPullChunkVecs = 4096;  // 64 KiB work units
+
+__device__ __forceinline__ uint32_t archiveBytes(int kind, const uint8_t* a) {
+  uint32_t extra = 0;
+  if (kind != kKindBytes) {
+    const uint4 fh = __ldg(reinterpret_cast<const uint4*>(a));
+    if (fh.x != kFloatMagicVersion) return 32u;
+    extra = kFloatHeaderBytes + floatNonCompBytes(kind, fh.y);
+  }
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(a + extra));
+  if (h.x != kAnsMagicVersion) return extra + 32u;
+  const uint64_t total = (uint64_t)extra + ansOverhead(h.y) + 2ull * h.w;
+  return total > 0xfffffff0ull ? 32u : (uint32_t)total;
+}
+
+__global__ void __launch_bounds__(kPullThreads)
+pullArchivesKernel(const __grid_constant__ InlineMembers im, int kind, uint32_t* __restrict__ outBytes) {
+  __shared__ uint32_t sFirst[kInlineMembers + 1];  // first chunk of member i
+  __shared__ uint32_t sBytes[kInlineMembers];
+  const uint32_t t = threadIdx.x, n = im.count;
+  if (t < n) {
+    const uint32_t want = archiveBytes(kind, static_cast<const uint8_t*>(im.m[t].in));
+    const uint32_t b = min(want, im.m[t].size & ~15u);
+    sBytes[t] = b;
+    if (outBytes && blockIdx.x == 0) outBytes[t] = want;
+  }
+  __syncthreads();
+  if (t == 0) {
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < n; ++i) { sFirst[i] = c; c += divUp(sBytes[i] / 16u, kPullChunkVecs); }
+    sFirst[n] = c;
+  }
+  __syncthreads();
+  const uint32_t total = sFirst[n];
+  uint32_t m = 0;
+  for (uint32_t c = blockIdx.x; c < total; c += gridDim.x) {
+    while (sFirst[m + 1] <= c) ++m;
+    const uint32_t v0 = (c - sFirst[m]) * kPullChunkVecs;
+    const uint32_t v1 = min(sBytes[m] / 16u, v0 + kPullChunkVecs);
+    const uint4* __restrict__ src = static_cast<const uint4*>(im.m[m].in);
+    uint4* __restrict__ dst = static_cast<uint4*>(im.m[m].out);
+    uint32_t v = v0 + t;
+    for (; v + 3u * kPullThreads < v1; v += 4u * kPullThreads) {
+      const uint4 a = ldgNc(src + v), b = ldgNc(src + v + kPullThreads), cc = ldgNc(src + v + 2u * kPullThreads),
+                  d = ldgNc(src + v + 3u * kPullThreads);
+      dst[v] = a; dst[v + kPullThreads] = b; dst[v + 2u * kPullThreads] = cc; dst[v + 3u * kPullThreads] = d;
+    }
+    for (; v < v1; v += kPullThreads) dst[v] = ldgNc(src + v);
+  }
+}
+}  // namespace
+
+int pullArchives(int kind, uint32_t n, const void* const* src, void* const* dst, const uint32_t* capacity,
+                 uint32_t* outBytes_dev, cudaStream_t stream) {
+  if (n == 0) return DGB_OK;
+  if (!src || !dst || !capacity) return DGB_ERR_INVALID_ARG;
+  const int ctas = std::max(1, options().pull_ctas);
+  static thread_local InlineMembers im;
+  for (uint32_t i0 = 0; i0 < n; i0 += kInlineMembers) {
+    const uint32_t k = std::min(kInlineMembers, n - i0);
+    im.count = k;
+    for (uint32_t i = 0; i < k; ++i) {
+      if (!src[i0 + i] || !dst[i0 + i]) return DGB_ERR_INVALID_ARG;
+      if ((reinterpret_cast<uintptr_t>(src[i0 + i]) | reinterpret_cast<uintptr_t>(dst[i0 + i])) & 15u) return DGB_ERR_INVALID_ARG;
+      im.m[i].in = src[i0 + i];
+      im.m[i].out = dst[i0 + i];
+      im.m[i].size = capacity[i0 + i];
+      im.m[i].work0 = 0;
+    }
+    timerBegin(kSlotPull, stream);
+    pullArchivesKernel<<<ctas, kPullThreads, 0, stream>>>(im, kind, outBytes_dev ? outBytes_dev + i0 : nullptr);
+    DGB_CUDA_TRY(cudaGetLastError());
+    timerEnd(kSlotPull, stream);
+  }
+  return DGB_OK;
+}
+
 int getInfo(int kind, void* temp, size_t tempBytes, const void* const* in, bool inIsDevice,
             uint32_t n, uint32_t* outSizes, uint32_t* outTypes, uint32_t* outChecksum,
             cudaStream_t stream) {

@@ -215,6 +215,27 @@ def compress_data_simple(compress_as_float: bool, ts_in: Sequence[torch.Tensor],
     return [comp[i, :host[i]].clone() for i in range(len(ts_in))]
 
 
+def pull_archives(compress_as_float: bool, ts_src: Sequence[torch.Tensor], ts_dst: Sequence[torch.Tensor],
+                  float_dtype: Optional[torch.dtype] = None, out_bytes: Optional[torch.Tensor] = None) -> None:
+    """Copies each archive of ts_src (uint8 rows, e.g. views of a peer GPU's memory) into the matching row of
+    ts_dst, exactly as long as its header says (dgb_archives_pull): the transfer step of the compressed
+    collectives.  `float_dtype` names the float kind of the archives when compress_as_float."""
+    _check(len(ts_src) > 0 and len(ts_src) == len(ts_dst))
+    dev = ts_dst[0].device
+    for a, b in zip(ts_src, ts_dst):
+        _check(a.is_cuda and b.is_cuda and b.device == dev and a.dtype == torch.uint8 and b.dtype == torch.uint8)
+        _check(a.is_contiguous() and b.is_contiguous())
+    ft = _float_type(torch.empty(0, dtype=float_dtype)) if compress_as_float else 0
+    if out_bytes is not None:
+        _check(out_bytes.is_cuda and out_bytes.dtype == torch.int32 and out_bytes.numel() >= len(ts_src))
+    with torch.cuda.device(dev):
+        rc = capi.lib().dgb_archives_pull(ft, len(ts_src), capi.ptr_array([t.data_ptr() for t in ts_src]),
+                                          capi.ptr_array([t.data_ptr() for t in ts_dst]),
+                                          capi.u32_array([t.numel() for t in ts_dst]),
+                                          out_bytes.data_ptr() if out_bytes is not None else None, _stream())
+    capi.check(rc, "pull_archives")
+
+
 # ----------------------------------------------------------- decompress ----
 
 def _validate_status(out_status, out_sizes, n, dev):

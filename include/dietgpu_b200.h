@@ -189,6 +189,17 @@ int dgb_copy_async(void* dst, const void* src, size_t bytes, void* stream);
 int dgb_copy_rows_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
                         size_t width_bytes, size_t rows, void* stream);
 
+/* ---- archive mover (new; for the compressed collectives) -------------------- */
+/* Copies num_in_batch archives from src[i] to dst[i] (host arrays of device pointers, 16 B aligned), each
+ * exactly as long as its own header says and at most dst_capacity[i] bytes: float_type 0 = ANS archives
+ * (ans/GpuANSUtils.cuh:67-227 header), DGB_FLOAT16/BFLOAT16/FLOAT32 = float archives
+ * (float/GpuFloatUtils.cuh:26-74).  src may be memory of a peer GPU mapped into this process (NVLink):
+ * sizes are read on the device, nothing travels to the host; out_bytes_dev (optional, device, [n]) receives
+ * the archive sizes.  An archive with a bad header is copied as its first 32 bytes so that the decoder
+ * which follows reports it.  The reference has no counterpart (it names the use, README.md:72,103-104). */
+int dgb_archives_pull(int float_type, uint32_t num_in_batch, const void* const* src, void* const* dst,
+                      const uint32_t* dst_capacity, uint32_t* out_bytes_dev, void* stream);
+
 /* ---- tuning knob (benchmarks / tests only) ------------------------------- */
 /* Selects an internal kernel variant by name ("decode_stage", "hist_mode" ...).
  * Unknown names return DGB_ERR_INVALID_ARG.  Defaults are the tuned choice. */
@@ -196,7 +207,7 @@ int dgb_set_option(const char* name, int value);
 int dgb_get_option(const char* name, int* value);
 /* With option "timing" = 1 every kernel launch is bracketed by CUDA events on the caller's
  * stream; this returns (and resets) the summed durations in ms and launch counts per kernel:
- * slot 0 stats (K1), 1 encode (K2), 2 plan, 3 decode, 4 checksum, 5 fused encode.  Synchronises the device. */
+ * slot 0 stats (K1), 1 encode (K2), 2 plan, 3 decode, 4 checksum, 5 fused encode, 6 archive mover.  Synchronises the device. */
 int dgb_kernel_times(float* ms, int* counts, int nslots);
 
 #ifdef __cplusplus

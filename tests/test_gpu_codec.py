@@ -539,6 +539,46 @@ def test_calls_can_be_captured_into_a_cuda_graph():
         assert sizes.cpu().tolist() == want
 
 
+def test_archive_mover_copies_exactly_the_archive():
+    # dgb_archives_pull: each archive is copied as long as its header says (sizes read on the device), the rest
+    # of the destination row is left alone; bad headers arrive as 32 bytes and fail in the decoder
+    from dietgpu_b200 import ops
+
+    for as_float, dt in ((True, torch.bfloat16), (True, torch.float32), (False, torch.uint8)):
+        if as_float:
+            ts = [torch.randn(30000 + 4097 * i, device="cuda").to(dt) for i in range(5)]
+        else:
+            ts = [to_dev_bytes(zipf_bytes(50000 + 977 * i, 1.2, i)) for i in range(5)]
+        comp, sizes, _ = ops.compress_data(as_float, ts)
+        hs = sizes.cpu().tolist()
+        dst = torch.full_like(comp, 0xAB)
+        got = torch.zeros(len(ts), dtype=torch.int32, device="cuda")
+        ops.pull_archives(as_float, [comp[i] for i in range(len(ts))], [dst[i] for i in range(len(ts))], dt, got)
+        assert got.cpu().tolist() == hs
+        for i, k in enumerate(hs):
+            assert torch.equal(dst[i, :k], comp[i, :k])
+            assert bool((dst[i, k:] == 0xAB).all())
+        outs = [torch.empty_like(t) for t in ts]
+        st = torch.zeros(len(ts), dtype=torch.uint8, device="cuda")
+        ops.decompress_data(as_float, [dst[i] for i in range(len(ts))], outs, False, None, st)
+        assert bool(st.all())
+        for a, b in zip(ts, outs):
+            assert torch.equal(a.view(torch.uint8), b.view(torch.uint8))
+        # a corrupted magic: 32 bytes arrive, the decoder reports the member
+        bad = comp.clone()
+        bad[2, 0] ^= 0xFF
+        dst.fill_(0)
+        ops.pull_archives(as_float, [bad[i] for i in range(len(ts))], [dst[i] for i in range(len(ts))], dt, got)
+        assert got.cpu().tolist()[2] == 32 and not bool(dst[2, 32:].any())
+        st.zero_()
+        ops.decompress_data(as_float, [dst[i] for i in range(len(ts))], outs, False, None, st)
+        assert st.cpu().tolist() == [1, 1, 0, 1, 1]
+        # a destination shorter than the archive: cut at the capacity, nothing written behind it
+        small = torch.zeros(hs[0] + 64, dtype=torch.uint8, device="cuda")
+        ops.pull_archives(as_float, [comp[0]], [small[:hs[0] - 160]], dt)
+        assert torch.equal(small[:hs[0] - 160], comp[0, :hs[0] - 160]) and not bool(small[hs[0] - 160:].any())
+
+
 def test_get_compressed_info_matches_oracle():
     # dgb_{ans,float}_get_compressed_info (ans/GpuANSInfo.cu:14-49, float/GpuFloatInfo.cu:17-64) against
     # dgo_ans_info / dgo_float_info on the same archives: uncompressed sizes, float types, stored checksums

@@ -24,7 +24,7 @@ def _worker(rank, world, port, backend, q):
 
         ok = True
         # peer-memory transport (NVLink pull by the decode kernel): needs one GPU per rank
-        ws = dg.PeerWorkspace(4 << 20) if backend == "nccl" else None
+        ws = dg.PeerWorkspace(32 << 20) if backend == "nccl" else None
         for dt, n in ((torch.bfloat16, 300001), (torch.float16, 70000), (torch.uint8, 123457)):
             def make(r):
                 g = torch.Generator(device="cpu").manual_seed(1000 + r)
@@ -49,8 +49,8 @@ def _worker(rank, world, port, backend, q):
             for s in range(world):
                 ok = ok and torch.equal(recv[s].view(torch.uint8), chunk(s, rank).to(dev).view(torch.uint8))
             if ws is not None:
-                for _ in range(3):  # both halves of the workspace, and a reuse
-                    got = dg.all_gather_compressed(mine, members=6, peer=ws)
+                for mode, stages in (("push", 1), ("push", 2), ("push", 3), ("pull", 2), ("direct", 1), ("push", 2)):
+                    got = dg.all_gather_compressed(mine, members=6, peer=ws, peer_mode=mode, stages=stages)
                     ok = ok and torch.equal(got.view(torch.uint8), want.view(torch.uint8))
 
                 def reg(src, dst):  # regular all-to-all: one length
@@ -59,10 +59,14 @@ def _worker(rank, world, port, backend, q):
                         return torch.randn(40001, generator=g).to(dt)
                     return torch.randint(0, 9, (40001,), generator=g, dtype=torch.int32).to(dt)
 
-                recv = dg.all_to_all_compressed([reg(rank, d).to(dev) for d in range(world)], peer=ws)
-                for s in range(world):
-                    ok = ok and torch.equal(recv[s].view(torch.uint8), reg(s, rank).to(dev).view(torch.uint8))
+                for mode in ("pull", "direct"):
+                    recv = dg.all_to_all_compressed([reg(rank, d).to(dev) for d in range(world)], peer=ws, peer_mode=mode)
+                    for s in range(world):
+                        ok = ok and torch.equal(recv[s].view(torch.uint8), reg(s, rank).to(dev).view(torch.uint8))
         q.put((rank, bool(ok)))
+    except Exception as ex:  # noqa: BLE001  (report instead of leaving the parent to time out)
+        q.put((rank, f"{type(ex).__name__}: {ex}"))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -78,8 +82,8 @@ def test_two_rank_compressed_collectives():
     procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in range(world))
+    res = dict(q.get(timeout=150) for _ in range(world))
+    assert res == {0: True, 1: True}, (backend, res)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert res == {0: True, 1: True}, (backend, res)
