@@ -23,12 +23,22 @@ Two transports:
     all-gather of 64 MiB per rank takes 0.21 ms and this one 0.77 ms, so it pays on links slower than
     ~100 GB/s (inter-node), which is where the reference aims it.
   * peer memory (`PeerWorkspace`, one node, NVLink / NVSwitch): every rank encodes into a buffer its peers
-    have mapped (torch symmetric memory: CUDA VMM handles exchanged once at set-up), one device-side
-    barrier, and then the DECODE KERNEL ITSELF reads the peers' archives over NVLink -- its TMA bulk
-    copies and cp.async rings take peer addresses like local ones, so the transfer is the decoder's own
-    input traffic, block by block, and needs no copy kernel, no packing, no size exchange (the decoder
-    reads sizes from the archive headers) and no host synchronisation.  A rank encodes ONCE and every
-    peer pulls, so the codec cost is amortised over world - 1 links (profiles/r02_allgather_p2p.txt).
+    have mapped (torch symmetric memory: CUDA VMM handles exchanged once at set-up); no packing, no size
+    exchange (sizes are read from the archive headers on the device), no host synchronisation, CUDA-graph
+    capturable.  Three ways to move the bytes, all bit-exact (tests/test_gpu_collectives.py):
+      "pull"   one device-side barrier, then the archive mover (dgb_archives_pull: a 64-CTA kernel that copies
+               exactly each archive's bytes) reads the peers' archives on a side stream, unit u+1 while the
+               decoder works on unit u from local memory;
+      "push"   no barrier: as soon as a group of members is coded the mover writes it into every peer's inbox
+               and raises a flag there; receivers decode a group when its flag is up;
+      "direct" one barrier, then the decode kernel itself reads the peers' archives (its TMA bulk copies and
+               cp.async rings take peer addresses like local ones).
+    Measured (profiles/r02_allgather_p2p_{2,8}gpu.txt, 256 MiB of bf16 per rank, ratio 0.674): 8 GPUs: plain
+    NCCL 3.03 ms, pull 2.87 ms (2.73 replayed from a CUDA graph: 1.11 x plain), push 3.80, direct 3.96;
+    2 GPUs: plain NCCL 0.62 ms, push 0.62, pull 0.70, direct 0.84.  The limits: an SM-driven copy over NVLink
+    reaches 550-570 GB/s here (the copy engines 728), and the decoder reading peer memory directly is
+    latency-bound at 326 GB/s.  A rank encodes once and every peer fetches, so the codec cost is amortised over
+    world - 1 links: at 64 MiB per rank the fixed costs still lose (0.72 x plain at 8 GPUs).
 """
 from __future__ import annotations
 
@@ -311,15 +321,16 @@ def _split(n: int, parts: int, quantum: int) -> List[int]:
 def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksum: bool = False,
                           temp_mem: Optional[torch.Tensor] = None, stages: int = 2,
                           peer: Optional[PeerWorkspace] = None, check: bool = True,
-                          peer_mode: str = "push") -> torch.Tensor:
+                          peer_mode: str = "pull") -> torch.Tensor:
     """Every rank contributes the CUDA tensor `t` (same shape and dtype on every rank; fp16 / bf16 / fp32 go
     through the float codec, anything else through the byte codec) and receives the concatenation
     [world * t.numel()] in rank order, bit-exact.  `members` = archives per rank (the codec's parallelism
     comes from blocks, so a handful is enough); `stages` = pipeline pieces (see the module docstring).
     With `peer` (a PeerWorkspace of the same group) the archives move through peer-mapped memory instead of a
-    collective; `peer_mode` = "push" (the archive mover writes each coded group into the peers' inboxes and flags
-    it), "pull" (after a barrier the mover reads the peers' archives, unit u+1 while unit u is decoded) or
-    "direct" (after a barrier the decode kernel reads peer memory itself); `stages` = pipeline groups;
+    collective; `peer_mode` = "pull" (after a barrier the archive mover reads the peers' archives, unit u+1 while
+    unit u is decoded; the fastest at 8 GPUs), "push" (the mover writes each coded group into the peers' inboxes
+    and flags it; no barrier; the fastest at 2 GPUs) or "direct" (after a barrier the decode kernel reads peer
+    memory itself); `stages` = pipeline groups per peer;
     `check=False` then skips the only host synchronisation (the read of the decode status)."""
     if not t.is_cuda or not t.is_contiguous():
         raise ValueError("all_gather_compressed: contiguous CUDA tensor expected (no CPU fallback)")

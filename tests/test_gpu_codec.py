@@ -579,6 +579,52 @@ def test_archive_mover_copies_exactly_the_archive():
         assert torch.equal(small[:hs[0] - 160], comp[0, :hs[0] - 160]) and not bool(small[hs[0] - 160:].any())
 
 
+def test_members_near_the_format_limit():
+    # one member of 1.5 Gi + 1 symbols: the largest round size whose worst-case archive still fits the format's
+    # 32-bit sizes (dgb_*_max_compressed_size != 0); 393 217 blocks, block offsets above 2^31 bytes in the
+    # float output.  Round trip, status, reported size against the archive's own header fields.
+    from dietgpu_b200 import ops
+
+    n = (3 << 29) + 1
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    for as_float in (False, True):
+        if as_float:
+            x = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+            for a in range(0, n, 1 << 28):
+                b = min(n, a + (1 << 28))
+                x[a:b] = torch.randn(b - a, generator=gen, device="cuda").to(torch.bfloat16)
+        else:
+            x = torch.empty(n, dtype=torch.uint8, device="cuda")
+            for a in range(0, n, 1 << 28):
+                b = min(n, a + (1 << 28))
+                x[a:b] = (torch.randn(b - a, generator=gen, device="cuda") * 12).abs().clamp(max=255).to(torch.uint8)
+        comp, sizes, _ = ops.compress_data(as_float, [x])
+        size = int(sizes[0])
+        words = comp[0, :size]
+        if as_float:
+            fh = words[:16].view(torch.int32).cpu().tolist()
+            assert (fh[0] & 0xffffffff) == 0xf00f0001 and fh[1] == n
+            ans = words[16 + ((n + 15) // 16) * 16:]
+        else:
+            ans = words
+        h = ans[:16].view(torch.int32).cpu().tolist()
+        nb = (n + 4095) // 4096
+        assert (h[0] & 0xffffffff) == 0xd00d0001 and h[1] == nb and h[2] == n
+        total_words = h[3] & 0xffffffff
+        overhead = 32 + 512 + 128 * nb + 8 * ((nb + 1) // 2 * 2)
+        assert ans.numel() == overhead + 2 * total_words
+        assert 0.2 * n < 2 * total_words < 1.0 * n
+        out = torch.empty_like(x)
+        st = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        osz = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops.decompress_data(as_float, [words], [out], False, None, st, osz)
+        assert st.item() == 1 and osz.item() == n
+        for a in range(0, n, 1 << 28):  # chunked compare keeps the temporaries small
+            b = min(n, a + (1 << 28))
+            assert torch.equal(x[a:b].view(torch.uint8 if not as_float else torch.int16), out[a:b].view(torch.uint8 if not as_float else torch.int16))
+        del x, out, comp, words, ans
+
+
 def test_get_compressed_info_matches_oracle():
     # dgb_{ans,float}_get_compressed_info (ans/GpuANSInfo.cu:14-49, float/GpuFloatInfo.cu:17-64) against
     # dgo_ans_info / dgo_float_info on the same archives: uncompressed sizes, float types, stored checksums

@@ -55,7 +55,7 @@ for mib in sizes_mib:
     ok = ok and torch.equal(gotp.view(torch.int16), want.view(torch.int16))
     t_push = {}
     for st_ in (1, 2, 4):
-        t_push[st_] = timed(lambda: dg.all_gather_compressed(x, members=members, peer=ws, temp_mem=temp, check=False, stages=st_))
+        t_push[st_] = timed(lambda: dg.all_gather_compressed(x, members=members, peer=ws, temp_mem=temp, check=False, stages=st_, peer_mode="push"))
     got3 = dg.all_gather_compressed(x, members=members, peer=ws, temp_mem=temp, peer_mode="direct")
     ok = ok and torch.equal(got3.view(torch.int16), want.view(torch.int16))
     t_direct = timed(lambda: dg.all_gather_compressed(x, members=members, peer=ws, temp_mem=temp, check=False, peer_mode="direct"))
@@ -82,8 +82,8 @@ for mib in sizes_mib:
             torch.cuda.synchronize(); dist.barrier()
             gp = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gp):
-                p1 = dg.all_gather_compressed(x, members=members, peer=ws, temp_mem=temp, check=False, stages=st_)
-                p2 = dg.all_gather_compressed(x, members=members, peer=ws, temp_mem=temp, check=False, stages=st_)
+                p1 = dg.all_gather_compressed(x, members=members, peer=ws, temp_mem=temp, check=False, stages=st_, peer_mode="push")
+                p2 = dg.all_gather_compressed(x, members=members, peer=ws, temp_mem=temp, check=False, stages=st_, peer_mode="push")
             t_graph_push[st_] = timed(gp.replay) / 2
             ok = ok and torch.equal(p1.view(torch.int16), want.view(torch.int16)) and torch.equal(p2.view(torch.int16), want.view(torch.int16))
     except Exception as ex:  # noqa: BLE001
