@@ -28,7 +28,7 @@ SYMBOLS = [
     "dgb_float_decompress_pointer", "dgb_float_decompress_split_size",
     "dgb_float_get_compressed_info",
     "dgb_copy_async", "dgb_copy_rows_async", "dgb_archives_pull",
-    "dgb_set_option", "dgb_get_option", "dgb_kernel_times",
+    "dgb_set_option", "dgb_get_option", "dgb_set_thread_option", "dgb_clear_thread_options", "dgb_kernel_times",
 ]
 
 
@@ -96,6 +96,10 @@ def lib():
     L.dgb_set_option.argtypes = [C.c_char_p, i32]
     L.dgb_get_option.restype = i32
     L.dgb_get_option.argtypes = [C.c_char_p, C.POINTER(i32)]
+    L.dgb_set_thread_option.restype = i32
+    L.dgb_set_thread_option.argtypes = [C.c_char_p, i32]
+    L.dgb_clear_thread_options.restype = i32
+    L.dgb_clear_thread_options.argtypes = []
     L.dgb_copy_async.restype = i32
     L.dgb_copy_async.argtypes = [vp, vp, sz, vp]
     L.dgb_copy_rows_async.restype = i32
@@ -119,6 +123,15 @@ def check(code: int, what: str) -> None:
 
 def set_option(name: str, value: int) -> None:
     check(lib().dgb_set_option(name.encode(), int(value)), f"set_option({name})")
+
+
+def set_thread_option(name: str, value: int) -> None:
+    """Override for codec calls made by the calling thread only (dgb_set_thread_option)."""
+    check(lib().dgb_set_thread_option(name.encode(), int(value)), f"set_thread_option({name})")
+
+
+def clear_thread_options() -> None:
+    check(lib().dgb_clear_thread_options(), "clear_thread_options")
 
 
 def get_option(name: str) -> int:

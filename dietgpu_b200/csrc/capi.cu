@@ -13,10 +13,13 @@
 
 namespace dgb {
 
-Options& options() {
-  static Options o;
-  return o;
-}
+// Tuning options: one process-wide set (dgb_set_option) and an optional per-thread copy that overrides it
+// (dgb_set_thread_option), so threads that drive different streams can run different variants without racing;
+// every codec call snapshots the effective set at entry.
+static Options gOptions;
+static thread_local Options tlsOptions;
+static thread_local bool tlsHasOptions = false;
+Options& options() { return tlsHasOptions ? tlsOptions : gOptions; }
 
 static thread_local cudaError_t tlsLastCuda = cudaSuccess;
 void setLastCudaError(cudaError_t e) { tlsLastCuda = e; }
@@ -381,8 +384,7 @@ int dgb_archives_pull(int float_type, uint32_t num_in_batch, const void* const* 
 
 // ---- options ---------------------------------------------------------------
 
-static int* optionSlot(const char* name) {
-  Options& o = options();
+static int* optionSlot(Options& o, const char* name) {
   if (!name) return nullptr;
   if (!std::strcmp(name, "decode_fused")) return &o.decode_fused;
   if (!std::strcmp(name, "decode_warps")) return &o.decode_warps;
@@ -408,9 +410,25 @@ static int* optionSlot(const char* name) {
 }
 
 int dgb_set_option(const char* name, int value) {
-  int* s = optionSlot(name);
+  int* s = optionSlot(dgb::gOptions, name);
   if (!s) return DGB_ERR_INVALID_ARG;
   *s = value;
+  return DGB_OK;
+}
+
+int dgb_set_thread_option(const char* name, int value) {
+  dgb::Options probe;
+  if (!optionSlot(probe, name)) return DGB_ERR_INVALID_ARG;
+  if (!dgb::tlsHasOptions) {
+    dgb::tlsOptions = dgb::gOptions;
+    dgb::tlsHasOptions = true;
+  }
+  *optionSlot(dgb::tlsOptions, name) = value;
+  return DGB_OK;
+}
+
+int dgb_clear_thread_options(void) {
+  dgb::tlsHasOptions = false;
   return DGB_OK;
 }
 
@@ -437,7 +455,7 @@ int dgb_get_option(const char* name, int* value) {
     *value = dgb::gLaunches.load(std::memory_order_relaxed);
     return DGB_OK;
   }
-  int* s = optionSlot(name);
+  int* s = optionSlot(dgb::options(), name);
   if (!s || !value) return DGB_ERR_INVALID_ARG;
   *value = *s;
   return DGB_OK;

@@ -432,7 +432,9 @@ __device__ __forceinline__ void decodeBlockWarp(uint32_t state, Stream st, uint3
   // groups of U full rows are walked from the top: group k covers rows [row0 - U*(k+1), row0 - U*k)
   const uint32_t row0 = row;
   const uint32_t groups = row0 / U;
-  // stored bytes of the first two groups are requested before anything else
+  // stored bytes of the first two groups are requested before anything else (the barrier: every lane is done
+  // reading the ring slots of the previous block)
+  __syncwarp();
   if (groups > 0) wr.issue(row0 - U, 0);
   cpAsyncCommit();
   if (groups > 1) wr.issue(row0 - 2 * U, 1);
@@ -445,10 +447,12 @@ __device__ __forceinline__ void decodeBlockWarp(uint32_t state, Stream st, uint3
   uint32_t slot = 0, slotNext = 2;  // ring slots of group k and of group k + 2
   for (uint32_t k = 0; k < groups; ++k) {
     row -= U;
+    cpAsyncWait<1>();  // group k has landed (group k + 1 may still be in flight)
+    // one warp barrier does both jobs: every lane sees group k, and every lane is done reading group k - 1,
+    // whose ring slot the request below overwrites (three slots: current + two in flight)
+    __syncwarp();
     if (k + 2 < groups) wr.issue(row - 2 * U, slotNext);
     cpAsyncCommit();
-    cpAsyncWait<2>();  // group k has landed (the two youngest may still be in flight)
-    __syncwarp();
     const Cursor c = wr.at(row, slot);
     G::run(state, lut, st, geMask, wr, c);
     slot = slot + 1 == kRingSlots ? 0u : slot + 1;

@@ -931,11 +931,13 @@ __device__ __forceinline__ uint32_t encodeBlockWarp(const uint8_t* __restrict__ 
       cpAsyncCommit();
       uint32_t slot = 0, slotNext = 2 % In::kRingSlots;
       for (uint32_t k = 0; k < groups; ++k) {
+        if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
+        cpAsyncWait<1>();  // group k has landed (group k + 1 may still be in flight)
+        // one warp barrier does both jobs: every lane sees group k, and every lane is done reading group
+        // k - 1, whose ring slot (three-slot ring) the request below overwrites
+        __syncwarp();
         if (k + 2 < groups) issue(k + 2, slotNext);
         cpAsyncCommit();
-        if (sp.area && wa - stageAddr > sp.limitBytes) spillOut(sp, stageAddr, stage, wa, lane);
-        cpAsyncWait<2>();
-        __syncwarp();
         const uint32_t slotAddr = ringAddr + slot * kGroupBytes;
         if (KIND != kKindBytes) In::storeGroup(slotAddr, planes, elem0 + k * (U * 32), lane);
         encodeGroup<WIDE, KIND>(state, slotAddr + lane * WB, rc, wa);

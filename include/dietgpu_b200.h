@@ -205,6 +205,11 @@ int dgb_archives_pull(int float_type, uint32_t num_in_batch, const void* const* 
  * Unknown names return DGB_ERR_INVALID_ARG.  Defaults are the tuned choice. */
 int dgb_set_option(const char* name, int value);
 int dgb_get_option(const char* name, int* value);
+/* Per-thread override: the first call copies the process-wide set into a copy that only codec calls made by
+ * THIS thread see (and dgb_get_option on this thread reports); dgb_clear_thread_options drops the copy.  Every
+ * codec call snapshots its effective set at entry, so changing options never affects a call in flight. */
+int dgb_set_thread_option(const char* name, int value);
+int dgb_clear_thread_options(void);
 /* With option "timing" = 1 every kernel launch is bracketed by CUDA events on the caller's
  * stream; this returns (and resets) the summed durations in ms and launch counts per kernel:
  * slot 0 stats (K1), 1 encode (K2), 2 plan, 3 decode, 4 checksum, 5 fused encode, 6 archive mover.  Synchronises the device. */

@@ -81,3 +81,28 @@ def test_ops_raise_without_gpu():
 
     with pytest.raises(RuntimeError):
         dg.compress_data(False, [torch.zeros(16, dtype=torch.uint8)])
+
+
+def test_thread_options_override_only_their_thread():
+    # dgb_set_thread_option: a per-thread copy of the tuning set; other threads keep the process-wide one
+    import threading
+
+    from dietgpu_b200 import capi
+
+    base = capi.get_option("encode_warps")
+    seen = {}
+
+    def worker():
+        capi.set_thread_option("encode_warps", base + 3)
+        seen["worker"] = capi.get_option("encode_warps")
+        capi.set_option("decode_warps", capi.get_option("decode_warps"))  # process-wide set still works from here
+        capi.clear_thread_options()
+        seen["worker_cleared"] = capi.get_option("encode_warps")
+
+    t = threading.Thread(target=worker)
+    t.start()
+    t.join()
+    assert seen == {"worker": base + 3, "worker_cleared": base}
+    assert capi.get_option("encode_warps") == base
+    with pytest.raises(capi.DietGpuError):
+        capi.set_thread_option("no_such_option", 1)
