@@ -86,8 +86,15 @@ void splitParts(const uint64_t* weight, uint32_t n, int parts, uint32_t* bounds)
   bounds[0] = 0;
   uint64_t acc = 0;
   uint32_t idx = 0;
+  // options first_part_pct / last_part_pct: size of the first / last sub-batch in percent of an equal share
+  // (100 = equal); the middle sub-batches share the rest equally
+  const int fp = parts > 2 ? std::max(10, std::min(200, options().first_part_pct)) : 100;
+  const int lp = parts > 2 ? std::max(10, std::min(200, options().last_part_pct)) : 100;
+  const uint64_t eq = total / (uint64_t)parts;
+  const uint64_t first = eq * (uint64_t)fp / 100u, last = eq * (uint64_t)lp / 100u;
+  const uint64_t mid = parts > 2 && total > first + last ? (total - first - last) / (uint64_t)(parts - 2) : eq;
   for (int p = 1; p < parts; ++p) {
-    const uint64_t target = total / (uint64_t)parts * (uint64_t)p;
+    const uint64_t target = parts > 2 ? first + mid * (uint64_t)(p - 1) : eq * (uint64_t)p;
     const uint32_t mustLeave = (uint32_t)(parts - p);  // one member for every later part
     while (idx + mustLeave < n && (idx < bounds[p - 1] + 1 || acc + weight[idx] / 2 <= target)) acc += weight[idx++];
     bounds[p] = idx;
@@ -404,6 +411,8 @@ static int* optionSlot(Options& o, const char* name) {
   if (!std::strcmp(name, "hist_ctas_per_sm")) return &o.hist_ctas_per_sm;
   if (!std::strcmp(name, "inline_members")) return &o.inline_members;
   if (!std::strcmp(name, "pull_ctas")) return &o.pull_ctas;
+  if (!std::strcmp(name, "first_part_pct")) return &o.first_part_pct;
+  if (!std::strcmp(name, "last_part_pct")) return &o.last_part_pct;
   if (!std::strcmp(name, "timing")) return &o.timing;
   if (!std::strcmp(name, "parts")) return &o.parts;
   return nullptr;

@@ -106,6 +106,8 @@ struct Options {
   int hist_slab_kb = 64;     // bytes of input per histogram CTA iteration
   int hist_ctas_per_sm = 32; // stats grid = this many CTAs per SM (each CTA loops over slabs)
   int parts = 0;             // sub-batches run on internal streams (0 = auto, 1 = off, max 4)
+  int first_part_pct = 100;  // size of the first / last sub-batch relative to an equal share (capi.cu splitParts)
+  int last_part_pct = 100;
   int pull_ctas = 64;        // grid of the archive mover (dgb_archives_pull): enough loads in flight for NVLink, few SMs
   int inline_members = 1;   // 1: member table inside the kernel parameters when the batch has <= 64 members
   int timing = 0;            // 1: bracket every kernel launch with CUDA events (bench.py roofline pass)

@@ -13,4 +13,5 @@ timeout 300 $NCU -k regex:encodeKernelFast -s 2 -c 1 -o gpurun_out/${T}_encode_c
 timeout 300 $NCU -k regex:statsFloatKernel -s 2 -c 1 -o gpurun_out/${T}_stats_c3 -f python tools/prof_one.py c3 3 parts=1 > /dev/null 2>&1
 timeout 300 $NCU -k regex:decodeFusedKernel -s 2 -c 1 -o gpurun_out/${T}_decode_c2 -f python tools/prof_one.py c2 3 > /dev/null 2>&1
 timeout 300 $NCU -k regex:encodeKernelFast -s 2 -c 1 -o gpurun_out/${T}_encode_c2 -f python tools/prof_one.py c2 3 parts=1 > /dev/null 2>&1
+{ for tool in memcheck racecheck; do echo "=== compute-sanitizer --tool $tool: device-level API example kernels (tests/test_gpu_device_api.py) ==="; timeout 600 compute-sanitizer --tool $tool --error-exitcode 3 --print-limit 6 python -m pytest tests/test_gpu_device_api.py -x -q -m gpu 2>&1 | grep -v "Warning: \|warn\|Host Frame\|host backtrace" | tail -6; echo "exit code: ${PIPESTATUS[0]}"; done; } > gpurun_out/${T}_sanitizer_device_api.txt 2>&1
 ls -la gpurun_out/${T}_*
