@@ -94,7 +94,7 @@ void splitParts(const uint64_t* weight, uint32_t n, int parts, uint32_t* bounds)
   const uint64_t first = eq * (uint64_t)fp / 100u, last = eq * (uint64_t)lp / 100u;
   const uint64_t mid = parts > 2 && total > first + last ? (total - first - last) / (uint64_t)(parts - 2) : eq;
   for (int p = 1; p < parts; ++p) {
-    const uint64_t target = parts > 2 ? first + mid * (uint64_t)(p - 1) : eq * (uint64_t)p;
+    const uint64_t target = (parts > 2 && (fp != 100 || lp != 100)) ? first + mid * (uint64_t)(p - 1) : eq * (uint64_t)p;
     const uint32_t mustLeave = (uint32_t)(parts - p);  // one member for every later part
     while (idx + mustLeave < n && (idx < bounds[p - 1] + 1 || acc + weight[idx] / 2 <= target)) acc += weight[idx++];
     bounds[p] = idx;
