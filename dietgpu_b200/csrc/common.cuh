@@ -90,7 +90,7 @@ struct __align__(16) EncEntryWide {
 // ---- tuning options (dgb_set_option) ---------------------------------------
 struct Options {
   int decode_fused = 1;      // 1: one persistent launch, CTAs lease members and warps claim blocks; 0: plan + decode kernels
-  int decode_warps = 8;      // single-launch decoder: warps per CTA (4 or 8)
+  int decode_warps = 0;      // single-launch decoder: warps per CTA (4, 8, 20 = byte archives only; 0 = auto)
   int decode_slot_words = 0; // TMA staging slot per warp in u16 words; 0 = auto
   int encode_warps = 8;      // warps per encode CTA (each warp is an independent worker)
   int encode_slot_words = 0; // staging slot of the fast encoder in u16 words; 0 = auto

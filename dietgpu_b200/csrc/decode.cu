@@ -906,9 +906,18 @@ template <int KIND, int PB>
 int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
                       uint32_t slotWordsOpt, uint8_t* outSuccess, uint32_t* outSize, bool checksum,
                       cudaStream_t stream) {
-  // warps per CTA = warps that share one LUT and meet at the barrier when a lease ends
-  if (options().decode_warps == 4)
+  // warps per CTA = warps that share one LUT and meet at the barrier when a lease ends.  Float kinds: 8 (4 and
+  // 10 / 20 measured: c3 146.5 / 142.1 / 151.2 us against 143.3).  Byte archives need the worst-case staging slot
+  // (5.1 KiB per warp), which caps 8-warp CTAs at 32 resident warps per SM; 20-warp CTAs reach 40 (c2: 242 ->
+  // 233.5 us) -- used when the members are long enough to keep 20 warps busy through a lease.
+  int w = options().decode_warps;
+  if (w == 0) w = (KIND == kKindBytes && totalChunks * 8u >= 160ull * n) ? 20 : 8;
+  if (w == 4)
     return launchDecodeFusedW<KIND, PB, 4>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+  if constexpr (KIND == kKindBytes) {
+    if (w == 20)
+      return launchDecodeFusedW<KIND, PB, 20>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
+  }
   return launchDecodeFusedW<KIND, PB, 8>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
 }
 

@@ -467,7 +467,7 @@ def test_kernel_variants_agree():
     a = [zipf_bytes(300000, 1.1, 5), exp_bytes(4097, 50, 6), zipf_bytes(1, 1.0, 7), np.zeros(0, np.uint8)]
     f = [normal_words(50000 + 13 * i, "bf16", i) for i in range(5)]
     names = ("encode_fused", "decode_fused", "fused_chunk_blocks", "fused_stats_every", "fused_stage",
-             "encode_warps", "encode_canonical", "inline_members")
+             "encode_warps", "encode_canonical", "inline_members", "decode_warps")
     defaults = {k: capi.get_option(k) for k in names}
     variants = [
         dict(encode_fused=0, decode_fused=0),
@@ -483,6 +483,9 @@ def test_kernel_variants_agree():
         dict(encode_fused=0, encode_warps=4),
         dict(encode_canonical=1),
         dict(encode_canonical=1, decode_fused=0),
+        dict(decode_warps=20),  # byte archives: 20-warp decoder CTAs (auto only for long members)
+        dict(decode_warps=8),
+        dict(decode_warps=4),
         dict(inline_members=0),  # member table uploaded to scratch instead of travelling in the kernel parameters
     ]
     try:

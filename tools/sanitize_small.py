@@ -31,6 +31,7 @@ VARIANTS = [
     {"encode_fused": 1},
     {"decode_fused": 0},
     {"inline_members": 0},
+    {"decode_warps": 20},
     {"encode_warps": 2, "decode_slot_words": 512, "encode_slot_words": 512},
 ]
 if os.environ.get("SAN_QUICK") == "1":
