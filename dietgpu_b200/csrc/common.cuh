@@ -222,20 +222,6 @@ __device__ __forceinline__ void bulkLoad(uint32_t dstSmem, const void* src, uint
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-// shared -> global bulk copy (bulk async-group completion)
-__device__ __forceinline__ void bulkStore(void* dst, uint32_t srcSmem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-               "r"(srcSmem), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulkWaitRead0() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulkPrefetchL2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-
 // block-wide exclusive scan of one value per thread for THREADS threads
 // (THREADS multiple of 32, <= 1024).  `warpSums` is smem of THREADS/32 words.
 template <int THREADS>

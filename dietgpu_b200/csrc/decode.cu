@@ -1,25 +1,14 @@
 // decode.cu -- batched rANS decode (bytes) and fused float decompress
-// (fp16/bf16/fp32) for sm_100a.  Two launches per call:
-//
-//   P   planKernel     reads every member's header(s), validates them,
-//                      writes outSuccess / outSize (ans/GpuANSDecode.cuh:
-//                      326-341 semantics) and builds the flat block index
-//                      (exclusive scan of block counts) the decode kernel
-//                      partitions.  The reference instead sizes its grid blind
-//                      (ans/GpuANSDecode.cuh:500-523) and runs a separate LUT
-//                      kernel through global memory (:405-476).
-//   D   decodeKernel   each CTA owns a contiguous run of 4 KiB blocks; it
-//                      builds the 2^pb-entry decode LUT of the member in
-//                      shared memory straight from the archive's pdf, then
-//                      every warp decodes whole blocks (ans/GpuANSDecode.cuh:
-//                      55-217, 274-297 restated).  The block's compressed
-//                      words and lane states are staged into shared memory
-//                      with one TMA bulk copy (cp.async.bulk + mbarrier) so
-//                      the loop-carried refill load is an LDS, not a global
-//                      load; float kinds join the decoded byte with the stored
-//                      byte(s) and write the float word directly (any
-//                      alignment -- the reference's two-pass path,
-//                      float/GpuFloatDecompress.cuh:622-694, is not needed).
+// (fp16/bf16/fp32) for sm_100a.  One launch per call (decodeFusedKernel, further down): a persistent grid
+// whose CTAs lease members (header checks and the 2^pb LUT from the archive's own pdf happen inside the
+// CTA) and whose warps claim 4 KiB blocks; lane states + compressed words of a block arrive by one TMA
+// bulk copy (cp.async.bulk + mbarrier), the 32-lane interleaved rANS decode of ans/GpuANSDecode.cuh:55-217
+// runs with table look-ups and the loop-carried refill load in shared memory, and float kinds join the
+// decoded byte with the stored byte(s) (cp.async ring) and store the float word in the same loop, at any
+// alignment (float/GpuFloatDecompress.cuh:22-179, float/GpuFloatUtils.cuh:100-204 join rules; the
+// reference's two-pass path, float/GpuFloatDecompress.cuh:622-694, is not needed).
+// The round-1 pair planKernel (header validation ans/GpuANSDecode.cuh:326-341, flat block offsets) +
+// decodeKernel (static split of the blocks) is kept behind option decode_fused=0.
 #include <algorithm>
 #include <cstring>
 #include <vector>

@@ -1,19 +1,20 @@
 // encode.cu -- batched rANS encode (bytes) and float compress (fp16/bf16/fp32)
 // for sm_100a.  Two launches per call, whatever the batch size:
 //
-//   K1  statsKernel      one pass over the raw input: 256-bin histogram (+ XOR
-//                        checksum; for floats also the exponent split that
-//                        writes the stored bytes straight into the archive and
-//                        the comp bytes into an L2-resident scratch row).  The
-//                        LAST CTA of each member (atomic ticket) normalises the
-//                        histogram, bit-identical to the reference
-//                        (ans/GpuANSStatistics.cuh:178-367), writes the pdf
-//                        into the archive and the encoder table to scratch.
+//   K1  stats*Kernel     a pure read of the raw input: 256-bin histogram of the coded byte, taken out of
+//                        the raw bytes / float words with one shift and one mask per element (+ XOR
+//                        checksum); float kinds also write the 16 B float header and zero the
+//                        padding of the stored plane(s).  The LAST CTA of each member (atomic
+//                        ticket) normalises the histogram, bit-identical to the reference
+//                        (ans/GpuANSStatistics.cuh:178-367), writes the pdf into the archive and
+//                        the encoder table to scratch.
 //   K2  encodeKernelFast one resident wave of CTAs, each owning a contiguous range of 4 KiB
 //                        blocks (one shared table load per member); each warp runs the
 //                        32-lane interleaved rANS state machine of its block
-//                        (ans/GpuANSEncode.cuh:49-211) into a shared-memory staging slot
-//                        and takes its place in the archive's data section with one 64-bit
+//                        (ans/GpuANSEncode.cuh:49-211) over the member's RAW words (cp.async ring; float
+//                        kinds write the stored plane(s) of the archive from the same ring slot, which
+//                        replaces the reference's split pass, float/GpuFloatCompress.cuh:280-365)
+//                        into a shared-memory staging slot and takes its place in the archive's data section with one 64-bit
 //                        atomic, so the words go from shared memory straight to their final
 //                        place (the reference's uncoalesced scratch, prefix-sum kernels and
 //                        coalesce kernel -- ans/GpuANSEncode.cuh:515-672,

@@ -201,8 +201,8 @@ int dgb_archives_pull(int float_type, uint32_t num_in_batch, const void* const* 
                       const uint32_t* dst_capacity, uint32_t* out_bytes_dev, void* stream);
 
 /* ---- tuning knob (benchmarks / tests only) ------------------------------- */
-/* Selects an internal kernel variant by name ("decode_stage", "hist_mode" ...).
- * Unknown names return DGB_ERR_INVALID_ARG.  Defaults are the tuned choice. */
+/* Selects an internal kernel variant by name ("parts", "encode_canonical", "decode_warps" ...; the list
+ * is in INTEGRATION.md section 4).  Unknown names return DGB_ERR_INVALID_ARG.  Defaults are the tuned choice. */
 int dgb_set_option(const char* name, int value);
 int dgb_get_option(const char* name, int* value);
 /* Per-thread override: the first call copies the process-wide set into a copy that only codec calls made by
