@@ -900,7 +900,9 @@ int launchDecodeFused(const DecodeScratch& sc, uint32_t n, uint64_t totalChunks,
   // (5.1 KiB per warp), which caps 8-warp CTAs at 32 resident warps per SM; 20-warp CTAs reach 40 (c2: 242 ->
   // 233.5 us) -- used when the members are long enough to keep 20 warps busy through a lease.
   int w = options().decode_warps;
-  if (w == 0) w = (KIND == kKindBytes && totalChunks * 8u >= 160ull * n) ? 20 : 8;
+  // (at 11 bits the LUT is 8 KiB and the slot 5.6 KiB per warp: a 20-warp CTA needs 126 KiB and fits once per
+  // SM -- bench detail c2p11 fell from 884 to 800 GB/s -- so the wide CTA is used up to 10 bits only)
+  if (w == 0) w = (KIND == kKindBytes && PB <= 10 && totalChunks * 8u >= 160ull * n) ? 20 : 8;
   if (w == 4)
     return launchDecodeFusedW<KIND, PB, 4>(sc, n, totalChunks, slotWordsOpt, outSuccess, outSize, checksum, stream);
   if constexpr (KIND == kKindBytes) {

@@ -1300,7 +1300,8 @@ encodeKernelFast(EncodeScratch sc, const __grid_constant__ InlineMembers im, int
 }
 
 // ---------------------------------------------------------------------------
-// Fused single-launch encoder (default).  One persistent grid; every CTA picks, at each step, one
+// Fused single-launch encoder (option encode_fused=1; measured no faster than the two-kernel path, DESIGN.md
+// section 4, so not the default).  One persistent grid; every CTA picks, at each step, one
 // of two kinds of work from two global counters:
 //   * a STATISTICS item  = one slab of one member (the body of K1 above: histogram (+ split, +
 //     checksum); the CTA that finishes a member normalises, publishes pdf + table and sets the
