@@ -170,6 +170,8 @@ class PeerWorkspace:
         key = (rank, offset, nbytes)
         v = self._views.get(key)
         if v is None:
+            if len(self._views) > 512:  # views are cheap to rebuild; do not grow without bound when sizes vary
+                self._views.clear()
             v = self._views[key] = self.hdl.get_buffer(rank, (nbytes,), torch.uint8, offset)
         return v
 
@@ -321,13 +323,13 @@ def _split(n: int, parts: int, quantum: int) -> List[int]:
 def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksum: bool = False,
                           temp_mem: Optional[torch.Tensor] = None, stages: int = 2,
                           peer: Optional[PeerWorkspace] = None, check: bool = True,
-                          peer_mode: str = "pull") -> torch.Tensor:
+                          peer_mode: str = "auto") -> torch.Tensor:
     """Every rank contributes the CUDA tensor `t` (same shape and dtype on every rank; fp16 / bf16 / fp32 go
     through the float codec, anything else through the byte codec) and receives the concatenation
     [world * t.numel()] in rank order, bit-exact.  `members` = archives per rank (the codec's parallelism
     comes from blocks, so a handful is enough); `stages` = pipeline pieces (see the module docstring).
     With `peer` (a PeerWorkspace of the same group) the archives move through peer-mapped memory instead of a
-    collective; `peer_mode` = "pull" (after a barrier the archive mover reads the peers' archives, unit u+1 while
+    collective; `peer_mode` = "auto" (push for two ranks, pull beyond), "pull" (after a barrier the archive mover reads the peers' archives, unit u+1 while
     unit u is decoded; the fastest at 8 GPUs), "push" (the mover writes each coded group into the peers' inboxes
     and flags it; no barrier; the fastest at 2 GPUs) or "direct" (after a barrier the decode kernel reads peer
     memory itself); `stages` = pipeline groups per peer;
@@ -342,8 +344,10 @@ def all_gather_compressed(t: torch.Tensor, group=None, members: int = 8, checksu
     bounds = _split(n, members, 8)
     members = len(bounds) - 1
     if peer is not None:
+        if peer_mode == "auto":  # measured: push wins with one peer, the pipelined pull with seven
+            peer_mode = "push" if peer.world <= 2 else "pull"
         if peer_mode not in ("push", "pull", "direct"):
-            raise ValueError("all_gather_compressed: peer_mode is 'push', 'pull' or 'direct'")
+            raise ValueError("all_gather_compressed: peer_mode is 'auto', 'push', 'pull' or 'direct'")
         if peer_mode == "push":
             out = _all_gather_push(flat, as_float, bounds, peer, checksum, temp_mem, check, stages)
         else:

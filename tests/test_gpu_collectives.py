@@ -49,7 +49,7 @@ def _worker(rank, world, port, backend, q):
             for s in range(world):
                 ok = ok and torch.equal(recv[s].view(torch.uint8), chunk(s, rank).to(dev).view(torch.uint8))
             if ws is not None:
-                for mode, stages in (("push", 1), ("push", 2), ("push", 3), ("pull", 2), ("direct", 1), ("push", 2)):
+                for mode, stages in (("push", 1), ("push", 2), ("push", 3), ("pull", 2), ("direct", 1), ("auto", 2)):
                     got = dg.all_gather_compressed(mine, members=6, peer=ws, peer_mode=mode, stages=stages)
                     ok = ok and torch.equal(got.view(torch.uint8), want.view(torch.uint8))
 
