@@ -182,3 +182,66 @@ def test_batch_baseline_equals_per_member_oracle():
         for a, o, d in zip(archs, outs, batch):
             assert np.array_equal(a, O.float_compress(ft, d, 10)), ft
             assert np.array_equal(o, d)
+
+
+# ---- property tests (hypothesis): any byte string, any precision ----------------------------------------------
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@st.composite
+def _byte_arrays(draw):
+    n = draw(st.sampled_from([0, 1, 2, 31, 32, 33, 4095, 4096, 4097, 8192, 12289]) | st.integers(0, 20000))
+    seed = draw(st.integers(0, 2**31 - 1))
+    shape = draw(st.sampled_from(["uniform", "few", "one", "skewed", "two-level"]))
+    rng = np.random.default_rng(seed)
+    if shape == "uniform":
+        a = rng.integers(0, 256, n)
+    elif shape == "few":
+        a = rng.choice(rng.integers(0, 256, draw(st.integers(1, 6))), n)
+    elif shape == "one":
+        a = np.full(n, draw(st.integers(0, 255)))
+    elif shape == "skewed":
+        a = np.minimum(rng.exponential(draw(st.floats(0.5, 60.0)), n), 255)
+    else:  # a dominant symbol plus a thin spread over the whole alphabet (pdf-1 symbols, the "add" branch)
+        a = np.where(rng.random(n) < 0.97, 7, rng.integers(0, 256, n))
+    return a.astype(np.uint8)
+
+
+@settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(data=_byte_arrays(), pb=st.sampled_from([9, 10, 11]), cks=st.booleans())
+def test_property_ans_roundtrip_any_bytes(data, pb, cks):
+    arch = O.ans_encode(data, pb, cks)
+    assert arch.size <= O.ans_max_compressed_size(data.size) or data.size == 0
+    assert arch.size % 16 == 0
+    info = O.ans_info(arch)
+    assert info["rc"] == 0 and info["uncompressed"] == data.size and info["prob_bits"] == pb and info["has_checksum"] == cks
+    rc, out, got = O.ans_decode(arch, pb, verify_checksum=cks)
+    assert rc == 0 and got == data.size and np.array_equal(out, data)
+    assert np.array_equal(arch, O.ans_encode(data, pb, cks))  # deterministic
+    p = O.parse_ans(arch)
+    assert int(np.sum(p["pdf"])) == ((1 << pb) if data.size else 0)
+    if data.size:
+        # a decoder handed too little room reports it (ans/GpuANSDecode.cuh:326-337) instead of writing past it
+        rc2, _, got2 = O.ans_decode(arch, pb, capacity=data.size - 1)
+        assert rc2 != 0 and got2 == data.size
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(n=st.integers(0, 9000), seed=st.integers(0, 2**31 - 1), scale=st.sampled_from([1e-3, 1.0, 300.0]),
+       kind=st.sampled_from(["bf16", "f16", "f32"]), cks=st.booleans())
+def test_property_float_roundtrip(n, seed, scale, kind, cks):
+    import torch
+
+    ft = {"bf16": O.BF16, "f16": O.F16, "f32": O.F32}[kind]
+    x = torch.randn(n, generator=torch.Generator().manual_seed(seed)) * scale
+    if kind == "f32":
+        w = x.view(torch.int32).numpy().view(np.uint32)
+    else:
+        w = x.to(torch.bfloat16 if kind == "bf16" else torch.float16).view(torch.int16).numpy().view(np.uint16)
+    arch = O.float_compress(ft, w, 10, cks)
+    assert arch.size <= O.float_max_compressed_size(ft, n) or n == 0
+    info = O.float_info(arch)
+    assert info["rc"] == 0 and info["size"] == n and info["float_type"] == ft
+    rc, out, got = O.float_decompress(ft, arch, 10, verify_checksum=cks)
+    assert rc == 0 and got == n and np.array_equal(out, w)
